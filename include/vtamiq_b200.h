@@ -1,0 +1,140 @@
+/* vtamiq_b200 — C-ABI of the B200 (sm_100a) VTAMIQ inference hot path.
+ *
+ * The reference (ch-andrei/VTAMIQ) is pure Python/PyTorch and has no FFI of its own; the functions
+ * below are what a `ctypes` binding inside the reference's modules would call in place of the ATen
+ * ops on the path.  Each entry cites the reference code it replaces
+ * (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / C++ types; every buffer is a caller-allocated DEVICE
+ *     pointer unless the parameter is documented as host memory;
+ *   - every call takes an explicit stream (a cudaStream_t passed as void*), is asynchronous with
+ *     respect to the host, allocates nothing, and is capturable in a CUDA graph;
+ *   - return value: 0 = ok, negative = error (VTQ_ERR_*); the message is kept per handle and read
+ *     with vtq_last_error_string();
+ *   - "16-bit" operands are IEEE fp16 (VTQ_F16) or bfloat16 (VTQ_BF16), chosen per call; all
+ *     accumulation, the residual stream, LayerNorm, softmax statistics, DiffNet and the head are fp32;
+ *   - row-major everywhere; a "token row" is one 768-wide hidden vector.  The ref and dist streams
+ *     of a batch of B pairs are stacked as 2B sequences: sequence index = img * B + b (img 0 = ref).
+ */
+#ifndef VTAMIQ_B200_H_
+#define VTAMIQ_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VTQ_ABI_VERSION 1
+
+enum vtq_status {
+  VTQ_OK = 0,
+  VTQ_ERR_INVALID = -1, /* bad argument / unsupported shape */
+  VTQ_ERR_CUDA = -2,    /* CUDA runtime or driver error (sticky errors included) */
+  VTQ_ERR_NO_DEVICE = -3 /* no sm_100 device: there is NO CPU fallback */
+};
+
+enum vtq_dtype { VTQ_F16 = 0, VTQ_BF16 = 1 };
+
+/* GEMM epilogues (vtq_gemm) */
+enum vtq_epilogue {
+  VTQ_EPI_BIAS_H = 0,      /* out16 = acc + bias                       (QKV projection)            */
+  VTQ_EPI_BIAS_GELU_H = 1, /* out16 = gelu_erf(acc + bias)             (fc1)                        */
+  VTQ_EPI_BIAS_F32 = 2,    /* out32 = acc + bias                       (patch embedding)            */
+  VTQ_EPI_BIAS_RESID_F32 = 3 /* out32 += gamma * (acc + bias), gamma optional (attn.out, fc2)       */
+};
+
+typedef struct vtq_ctx vtq_ctx;
+
+/* ---- handle -------------------------------------------------------------------------------- */
+int vtq_abi_version(void);
+/* Fails with VTQ_ERR_NO_DEVICE unless `device` is a compute-capability 10.x GPU. */
+int vtq_create(vtq_ctx** out, int device);
+int vtq_destroy(vtq_ctx* ctx);
+const char* vtq_last_error_string(const vtq_ctx* ctx); /* ctx may be NULL: error of the last failed vtq_create */
+/* number of kernels launched through this handle since creation (monotonic) */
+unsigned long long vtq_launch_count(const vtq_ctx* ctx);
+/* bytes of scratch vtq_diffnet_head needs for a batch of B pairs */
+int64_t vtq_workspace_bytes(const vtq_ctx* ctx, int B, int hidden);
+
+/* ---- K1: patch extraction --------------------------------------------------------------------
+ * replaces data/patch_sampling.py:529-545 (gather closure), :559-568 (uv), :572-574 (scale ids).
+ *
+ * images   [n_img][3][H][W] fp32, one pyramid level.  Image i uses coordinate set (i % n_set).
+ * samples  [n_set][2][n] float64 — row 0 = y (top), row 1 = x (left) of each patch, un-truncated, exactly
+ *          as stratified_grid_sampling returns them (patch_sampling.py:224).
+ * Patch p of this level lands in slot (patch_offset + p) of N_total.  Any output pointer may be NULL.
+ *   patches_f32 [n_img][N_total][3][16][16]  bit-exact copy of the reference gather
+ *   patches_16  [n_img][N_total][768]        same values rounded to `dtype` (A operand of the embed GEMM)
+ *   pos         [n_img][N_total][2]  fp32 uv, = clamp((s + 8) / (dim - 8), 0, 1 - 1e-6) evaluated in fp64
+ *   scales      [n_img][N_total]     fp32 scale id (the reference casts its int ids to fp32, train.py:254)
+ */
+int vtq_patch_gather(vtq_ctx* ctx, const float* images, int n_img, int H, int W, const double* samples, int n_set,
+                     int n, int patch_offset, int N_total, float* patches_f32, void* patches_16, int dtype,
+                     float* pos, float* scales, int scale_id, void* stream);
+
+/* 2x2 mean pyramid level, floor mode, summation order ((a00+a01)+a10)+a11 then *0.25
+ * replaces nn.AvgPool2d(2) at data/patch_sampling.py:552,:600.  src [planes][H][W] -> dst [planes][H/2][W/2] */
+int vtq_avgpool2x2(vtq_ctx* ctx, const float* src, float* dst, int planes, int H, int W, void* stream);
+
+/* fp32 patches (the reference's model input, [rows][768]) -> 16-bit GEMM operand */
+int vtq_cast_rows(vtq_ctx* ctx, const float* src, void* dst16, int64_t n_elems, int dtype, void* stream);
+
+/* ---- K2: embedding assembly -------------------------------------------------------------------
+ * replaces modules/VisionTransformer/transformer.py:396-400 (scale index), :417-426 (uv index),
+ * :507-524 (tokens), :536-558 (sums + concat).
+ *
+ * proj      [n_seq*N][768] fp32   patch projection incl. conv bias (output of vtq_gemm, VTQ_EPI_BIAS_F32)
+ * pos       [n_seq*N][2]   fp32 uv;     scales [n_seq*N] fp32 or NULL
+ * pos_table [grid*grid+1][768]; scale_table [num_scales+1][768] or NULL
+ * cls_token [768] or NULL, extra_tokens [n_extra][768] or NULL;  T = (cls?1:0) + n_extra
+ * x         [n_seq][T+N][768] fp32 residual stream (written)
+ * pos_idx / scale_idx  optional int32 [n_seq*N] dumps of the gathered row indices (parity tests)
+ */
+int vtq_embed_assemble(vtq_ctx* ctx, const float* proj, const float* pos, const float* scales,
+                       const float* pos_table, int grid, const float* scale_table, int num_scales,
+                       const float* cls_token, const float* extra_tokens, int n_extra, int n_seq, int N,
+                       int hidden, float* x, int32_t* pos_idx, int32_t* scale_idx, void* stream);
+
+/* ---- K4: LayerNorm, fp32 rows -> 16-bit rows ----------------------------------------------------
+ * replaces nn.LayerNorm(768, eps=1e-6) at transformer.py:253-254,:276,:281 (encoder_norm: see K7). */
+int vtq_layernorm(vtq_ctx* ctx, const float* x, const float* weight, const float* bias, float eps, int64_t rows,
+                  int hidden, void* out16, int dtype, void* stream);
+
+/* ---- K3/K5: dense projection on tcgen05 ----------------------------------------------------------
+ * out = epilogue(A[M][K] * W[N][K]^T + bias[N]).  A, W 16-bit (lda/ldw = K unless lda given), fp32 accumulate
+ * in TMEM.  replaces F.conv2d patch projection (transformer.py:532), Linear query/key/value (:154-156, fused
+ * as one N=3*hidden GEMM), Linear out (:169) + residual (:279), fc1+GELU (:213), fc2 (:214) + residual (:284).
+ * K % 64 == 0, N % 64 == 0; any M >= 1.  ldo in elements of the output type. */
+int vtq_gemm(vtq_ctx* ctx, const void* A, int64_t lda, const void* W, const float* bias, int M, int N, int K,
+             int dtype, int epilogue, void* out, int64_t ldo, const float* gamma, void* stream);
+
+/* ---- K6: fused multi-head self-attention -----------------------------------------------------------
+ * replaces transformer.py:158-166: softmax(Q K^T / sqrt(64)) V per (sequence, head), never materialising S x S.
+ * qkv [n_seq*S][3*heads*64] 16-bit rows = [q | k | v];  out [n_seq*S][heads*64] 16-bit (head-concatenated). */
+int vtq_attention_fwd(vtq_ctx* ctx, const void* qkv, void* out, int n_seq, int S, int heads, int dtype,
+                      void* stream);
+
+/* ---- K7: final LayerNorm of the quality token + difference ----------------------------------------
+ * replaces encoder_norm on the used token (transformer.py:376,:634) and modules/vtamiq/vtamiq.py:104-111.
+ * x [2*B][S][hidden] fp32; diff[b] = gamma * (LN(x[b][token]) - LN(x[B+b][token])); gamma may be NULL. */
+int vtq_cls_diff(vtq_ctx* ctx, const float* x, int B, int S, int hidden, int token, const float* ln_weight,
+                 const float* ln_bias, float eps, const float* gamma, float* diff, void* stream);
+
+/* ---- K8: DiffNet + quality head ------------------------------------------------------------------------
+ * replaces modules/RCAN/channel_attention.py:13-86 as instantiated by modules/vtamiq/vtamiq.py:12-23, and the
+ * q_predictor of vtamiq.py:71-77,:114-117.  All fp32.
+ * params: HOST array of device pointers, in this order:
+ *   for g in [0,num_rgs): for r in [0,num_rcabs): prelu_a, W1, b1, Wdown, bdown, Wup, bup ; then Wg, bg
+ *   then Wf, bf (final conv; both NULL if num_rgs == 0 i.e. calibrate=False)
+ *   then Wh, bh, prelu_h, Wq, bq (head: hidden -> hidden/4 -> 1)
+ * diff [B][hidden] (read), q [B] (written), workspace >= vtq_workspace_bytes(B, hidden). */
+int vtq_diffnet_head(vtq_ctx* ctx, const float* diff, const void* const* params, int n_params, int num_rgs,
+                     int num_rcabs, int hidden, int ca_hidden, int head_hidden, int B, float* q, void* workspace,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VTAMIQ_B200_H_ */

@@ -1,0 +1,21 @@
+"""Shim for `timm.layers`: DropPath (identity at inference / p=0) and trunc_normal_."""
+import torch
+from torch import nn
+
+trunc_normal_ = torch.nn.init.trunc_normal_
+
+
+class DropPath(nn.Module):
+    def __init__(self, drop_prob: float = 0., scale_by_keep: bool = True):
+        super().__init__()
+        self.drop_prob = drop_prob
+        self.scale_by_keep = scale_by_keep
+
+    def forward(self, x):
+        if self.drop_prob == 0. or not self.training:
+            return x
+        keep = 1. - self.drop_prob
+        mask = x.new_empty((x.shape[0],) + (1,) * (x.ndim - 1)).bernoulli_(keep)
+        if keep > 0. and self.scale_by_keep:
+            mask.div_(keep)
+        return x * mask

@@ -1,0 +1,112 @@
+// C-ABI plumbing: handle lifetime, error strings, tensor-map encoding, and the thin extern "C" wrappers around
+// the tcgen05 launchers.  No torch types cross this boundary (include/vtamiq_b200.h).
+#include "host.h"
+
+#include <cstdio>
+#include <mutex>
+
+namespace vtq {
+
+static std::string g_create_error;  // error of the last failed vtq_create (no handle exists yet)
+
+int fail(vtq_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->last_error = msg;
+  else g_create_error = msg;
+  return code;
+}
+
+int check_cuda(vtq_ctx* ctx, cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return VTQ_OK;
+  return fail(ctx, VTQ_ERR_CUDA, std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
+}
+
+int make_tensor_map(vtq_ctx* ctx, CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base,
+                    const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+  cuuint64_t gdims[5];
+  cuuint64_t gstrides[4];
+  cuuint32_t gbox[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdims[i] = dims[i];
+    gbox[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstrides[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = ctx->encode_tiled(out, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdims, gstrides,
+                                 gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof(buf),
+             "cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims [%llu,%llu,%llu] stride0 %llu box [%u,%u,%u]",
+             static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+             (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 1 ? strides_bytes[0] : 0),
+             box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0);
+    return fail(ctx, VTQ_ERR_CUDA, buf);
+  }
+  return VTQ_OK;
+}
+
+}  // namespace vtq
+
+using namespace vtq;
+
+extern "C" int vtq_abi_version(void) { return VTQ_ABI_VERSION; }
+
+extern "C" int vtq_create(vtq_ctx** out, int device) {
+  if (!out) return VTQ_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    cudaGetLastError();
+    return fail(nullptr, VTQ_ERR_NO_DEVICE, "vtq_create: no CUDA device visible; this library has no CPU fallback");
+  }
+  if (device < 0 || device >= count) return fail(nullptr, VTQ_ERR_INVALID, "vtq_create: device index out of range");
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return check_cuda(nullptr, e, "vtq_create");
+  if (prop.major != 10) {
+    return fail(nullptr, VTQ_ERR_NO_DEVICE,
+                std::string("vtq_create: device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                    std::to_string(prop.minor) + "; the kernels are compiled for sm_100a only");
+  }
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return check_cuda(nullptr, e, "vtq_create: cudaSetDevice");
+  vtq_ctx* ctx = new vtq_ctx();
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  ctx->smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+    delete ctx;
+    return fail(nullptr, VTQ_ERR_CUDA, "vtq_create: cuTensorMapEncodeTiled is not available from this driver");
+  }
+  ctx->encode_tiled = reinterpret_cast<decltype(ctx->encode_tiled)>(fn);
+  *out = ctx;
+  return VTQ_OK;
+}
+
+extern "C" int vtq_destroy(vtq_ctx* ctx) {
+  delete ctx;
+  return VTQ_OK;
+}
+
+extern "C" const char* vtq_last_error_string(const vtq_ctx* ctx) {
+  return ctx ? ctx->last_error.c_str() : g_create_error.c_str();
+}
+
+extern "C" unsigned long long vtq_launch_count(const vtq_ctx* ctx) { return ctx ? ctx->launches : 0ull; }
+
+extern "C" int vtq_gemm(vtq_ctx* ctx, const void* A, int64_t lda, const void* W, const float* bias, int M, int N,
+                        int K, int dtype, int epilogue, void* out, int64_t ldo, const float* gamma, void* stream) {
+  if (!ctx) return VTQ_ERR_INVALID;
+  return launch_gemm(ctx, A, lda, W, bias, M, N, K, dtype, epilogue, out, ldo, gamma,
+                     static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vtq_attention_fwd(vtq_ctx* ctx, const void* qkv, void* out, int n_seq, int S, int heads, int dtype,
+                                 void* stream) {
+  if (!ctx) return VTQ_ERR_INVALID;
+  return launch_attention(ctx, qkv, out, n_seq, S, heads, dtype, static_cast<cudaStream_t>(stream));
+}

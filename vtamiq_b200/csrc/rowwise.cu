@@ -1,0 +1,397 @@
+// HBM-bound kernels of the path: K1 patch gather (+uv, scale ids), 2x2 mean pyramid, fp32->16-bit cast,
+// K2 embedding assembly, K4 LayerNorm, K7 quality-token LayerNorm + difference.
+// All are one-pass, coalesced, 128-bit on the wide side; none has data reuse worth staging in smem.
+#include "common.cuh"
+#include "host.h"
+
+namespace vtq {
+
+constexpr int PATCH = 16;
+constexpr int PATCH_ELEMS = 3 * PATCH * PATCH;  // 768
+
+// ------------------------------------------------------------------------------------------------
+// K1: patch gather.  grid = (n patches, n_img); 192 threads, each moves 4 horizontally adjacent pixels:
+// 4 scalar loads (source x0 is only 4-byte aligned), one 128-bit fp32 store and/or one 64-bit 16-bit store.
+// Thread 0 also emits uv and the scale id.  Reference semantics: data/patch_sampling.py:529-545,:559-568.
+// ------------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void __launch_bounds__(192) patch_gather_kernel(const float* __restrict__ images, int H, int W,
+                                                           const double* __restrict__ samples, int n_set, int n,
+                                                           int patch_offset, int N_total,
+                                                           float* __restrict__ patches_f32,
+                                                           void* __restrict__ patches_16, float* __restrict__ pos,
+                                                           float* __restrict__ scales, float scale_id) {
+  const int p = blockIdx.x;
+  const int img = blockIdx.y;
+  const int set = img % n_set;
+  const double sy = samples[(static_cast<size_t>(set) * 2 + 0) * n + p];
+  const double sx = samples[(static_cast<size_t>(set) * 2 + 1) * n + p];
+  // torch advanced indexing with float64 indices truncates toward zero; coords are >= 0
+  const int y0 = static_cast<int>(sy);
+  const int x0 = static_cast<int>(sx);
+  const size_t slot = static_cast<size_t>(img) * N_total + patch_offset + p;
+
+  const int t = threadIdx.x;       // 0..191: (c, i, j4)
+  const int c = t >> 6;            // channel
+  const int i = (t >> 2) & 15;     // row inside the patch
+  const int j4 = (t & 3) * 4;      // first of 4 columns
+  const float* src = images + ((static_cast<size_t>(img) * 3 + c) * H + (y0 + i)) * W + x0 + j4;
+  const float v0 = __ldg(src + 0), v1 = __ldg(src + 1), v2 = __ldg(src + 2), v3 = __ldg(src + 3);
+  const size_t o = slot * PATCH_ELEMS + static_cast<size_t>(t) * 4;
+  if (patches_f32 != nullptr) *reinterpret_cast<float4*>(patches_f32 + o) = make_float4(v0, v1, v2, v3);
+  if (patches_16 != nullptr) {
+    uint2 h = make_uint2(pack2<DT>(v0, v1), pack2<DT>(v2, v3));
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(patches_16) + o) = h;
+  }
+  if (t == 0) {
+    if (pos != nullptr) {
+      // (sample + P/2) / (dim - P/2) in float64, clamp to [0, 1 - 1e-6], round once to fp32 on store
+      const double hi = 1.0 - 1e-6;
+      double u = (sy + 8.0) / static_cast<double>(static_cast<float>(H - 8));
+      double v = (sx + 8.0) / static_cast<double>(static_cast<float>(W - 8));
+      u = fmin(fmax(u, 0.0), hi);
+      v = fmin(fmax(v, 0.0), hi);
+      pos[slot * 2 + 0] = __double2float_rn(u);
+      pos[slot * 2 + 1] = __double2float_rn(v);
+    }
+    if (scales != nullptr) scales[slot] = scale_id;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2x2 mean, floor mode; the summation tree and the exact /4 follow ATen's avg_pool2d (kh outer, kw inner).
+// ------------------------------------------------------------------------------------------------
+__global__ void avgpool2x2_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int W, int Ho,
+                                  int Wo, size_t total) {
+  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int xo = static_cast<int>(idx % Wo);
+  const size_t rem = idx / Wo;
+  const int yo = static_cast<int>(rem % Ho);
+  const size_t plane = rem / Ho;
+  const float* s = src + (plane * H + 2 * yo) * static_cast<size_t>(W) + 2 * xo;
+  const float2 a = *reinterpret_cast<const float2*>(s);  // 2*xo even, W arbitrary: alignment handled below
+  const float2 b = *reinterpret_cast<const float2*>(s + W);
+  dst[idx] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(a.x, a.y), b.x), b.y), 0.25f);
+}
+
+__global__ void avgpool2x2_kernel_unaligned(const float* __restrict__ src, float* __restrict__ dst, int H, int W,
+                                            int Ho, int Wo, size_t total) {
+  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int xo = static_cast<int>(idx % Wo);
+  const size_t rem = idx / Wo;
+  const int yo = static_cast<int>(rem % Ho);
+  const size_t plane = rem / Ho;
+  const float* s = src + (plane * H + 2 * yo) * static_cast<size_t>(W) + 2 * xo;
+  dst[idx] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(__ldg(s), __ldg(s + 1)), __ldg(s + W)), __ldg(s + W + 1)),
+                       0.25f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 -> 16-bit, 8 elements per thread (2 x 128-bit loads, 1 x 128-bit store)
+// ------------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void cast_rows_kernel(const float* __restrict__ src, void* __restrict__ dst, size_t n8) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= n8) return;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i);
+  const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+  uint4 o = make_uint4(pack2<DT>(a.x, a.y), pack2<DT>(a.z, a.w), pack2<DT>(b.x, b.y), pack2<DT>(b.z, b.w));
+  reinterpret_cast<uint4*>(dst)[i] = o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: embedding assembly.  One warp per output token row (hidden/128 float4 per lane).
+//   token rows : cls + pos_table[0]  |  extra_tokens[k]
+//   patch rows : (proj + pos_table[idx]) + scale_table[sidx]      (same association as the reference)
+// Index arithmetic is the reference's fp32 arithmetic: floor(u*g)*g + floor(v*g) + 1; clamp(s,0,ns-1)+1.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) embed_assemble_kernel(
+    const float* __restrict__ proj, const float* __restrict__ pos, const float* __restrict__ scales,
+    const float* __restrict__ pos_table, int grid_w, const float* __restrict__ scale_table, int num_scales,
+    const float* __restrict__ cls_token, const float* __restrict__ extra_tokens, int T, int n_seq, int N, int hidden,
+    float* __restrict__ x, int32_t* __restrict__ pos_idx, int32_t* __restrict__ scale_idx) {
+  const int S = T + N;
+  const size_t row = blockIdx.x * static_cast<size_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= static_cast<size_t>(n_seq) * S) return;
+  const int lane = threadIdx.x & 31;
+  const int seq = static_cast<int>(row / S);
+  const int tok = static_cast<int>(row % S);
+  float4* dst = reinterpret_cast<float4*>(x + row * hidden);
+  const int nvec = hidden >> 2;
+  if (tok < T) {
+    const bool is_cls = (cls_token != nullptr) && tok == 0;
+    const float* base = is_cls ? cls_token : extra_tokens + static_cast<size_t>(tok - (cls_token ? 1 : 0)) * hidden;
+    for (int v = lane; v < nvec; v += 32) {
+      float4 a = __ldg(reinterpret_cast<const float4*>(base) + v);
+      if (is_cls && pos_table != nullptr) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(pos_table) + v);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      dst[v] = a;
+    }
+    return;
+  }
+  const size_t pr = static_cast<size_t>(seq) * N + (tok - T);
+  const float* prow = proj + pr * hidden;
+  const float* ptab = nullptr;
+  const float* stab = nullptr;
+  if (pos_table != nullptr) {
+    const float g = static_cast<float>(grid_w);
+    const float fu = floorf(__fmul_rn(pos[pr * 2 + 0], g));
+    const float fv = floorf(__fmul_rn(pos[pr * 2 + 1], g));
+    const float fidx = __fadd_rn(__fadd_rn(__fmul_rn(fu, g), fv), 1.0f);
+    const long long idx = static_cast<long long>(fidx);
+    if (lane == 0 && pos_idx != nullptr) pos_idx[pr] = static_cast<int32_t>(idx);
+    ptab = pos_table + static_cast<size_t>(idx) * hidden;
+  }
+  if (scale_table != nullptr) {
+    float s = scales[pr];
+    s = fminf(fmaxf(s, 0.0f), static_cast<float>(num_scales - 1)) + 1.0f;
+    const long long sidx = static_cast<long long>(s);
+    if (lane == 0 && scale_idx != nullptr) scale_idx[pr] = static_cast<int32_t>(sidx);
+    stab = scale_table + static_cast<size_t>(sidx) * hidden;
+  }
+  for (int v = lane; v < nvec; v += 32) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(prow) + v);
+    if (ptab != nullptr) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ptab) + v);
+      a.x = __fadd_rn(a.x, b.x); a.y = __fadd_rn(a.y, b.y); a.z = __fadd_rn(a.z, b.z); a.w = __fadd_rn(a.w, b.w);
+    }
+    if (stab != nullptr) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(stab) + v);
+      a.x = __fadd_rn(a.x, b.x); a.y = __fadd_rn(a.y, b.y); a.z = __fadd_rn(a.z, b.z); a.w = __fadd_rn(a.w, b.w);
+    }
+    dst[v] = a;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: LayerNorm over `hidden` (<= 1024, multiple of 128): one warp per row, the row stays in registers,
+// two-pass mean / variance with warp shuffles, 16-bit output (the A operand of the next GEMM).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int DT, int VPL /* float4 per lane */>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ b, float eps, size_t rows,
+                                                        void* __restrict__ out16) {
+  constexpr int HIDDEN = VPL * 128;
+  const size_t row = blockIdx.x * static_cast<size_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float4* src = reinterpret_cast<const float4*>(x + row * HIDDEN);
+  float4 v[VPL];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    v[k] = src[lane + 32 * k];
+    s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+  }
+  const float mean = warp_sum(s) * (1.0f / HIDDEN);
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const float dx = v[k].x - mean, dy = v[k].y - mean, dz = v[k].z - mean, dw = v[k].w - mean;
+    q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / HIDDEN) + eps);
+  uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(out16) + row * HIDDEN);
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(w) + lane + 32 * k);
+    const float4 be = __ldg(reinterpret_cast<const float4*>(b) + lane + 32 * k);
+    const float y0 = (v[k].x - mean) * rstd * g.x + be.x;
+    const float y1 = (v[k].y - mean) * rstd * g.y + be.y;
+    const float y2 = (v[k].z - mean) * rstd * g.z + be.z;
+    const float y3 = (v[k].w - mean) * rstd * g.w + be.w;
+    dst[lane + 32 * k] = make_uint2(pack2<DT>(y0, y1), pack2<DT>(y2, y3));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7: diff[b] = gamma * (LN(x[b][token]) - LN(x[B+b][token])), fp32.  One warp per pair.
+// Only the quality-token rows need the encoder_norm; 1/sqrt (not rsqrt.approx) keeps this fp32-faithful.
+// ------------------------------------------------------------------------------------------------
+template <int VPL>
+__global__ void __launch_bounds__(128) cls_diff_kernel(const float* __restrict__ x, int B, int S, int token,
+                                                       const float* __restrict__ w, const float* __restrict__ b,
+                                                       float eps, const float* __restrict__ gamma,
+                                                       float* __restrict__ diff) {
+  constexpr int HIDDEN = VPL * 128;
+  const int pair = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pair >= B) return;
+  const int lane = threadIdx.x & 31;
+  float4 y[2][VPL];
+#pragma unroll
+  for (int img = 0; img < 2; ++img) {
+    const size_t row = (static_cast<size_t>(img) * B + pair) * S + token;
+    const float4* src = reinterpret_cast<const float4*>(x + row * HIDDEN);
+    float4 v[VPL];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      v[k] = src[lane + 32 * k];
+      s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+    const float mean = warp_sum(s) / HIDDEN;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const float dx = v[k].x - mean, dy = v[k].y - mean, dz = v[k].z - mean, dw = v[k].w - mean;
+      q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) / HIDDEN + eps);
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(w) + lane + 32 * k);
+      const float4 be = __ldg(reinterpret_cast<const float4*>(b) + lane + 32 * k);
+      y[img][k].x = (v[k].x - mean) * rstd * g.x + be.x;
+      y[img][k].y = (v[k].y - mean) * rstd * g.y + be.y;
+      y[img][k].z = (v[k].z - mean) * rstd * g.z + be.z;
+      y[img][k].w = (v[k].w - mean) * rstd * g.w + be.w;
+    }
+  }
+  float4* dst = reinterpret_cast<float4*>(diff + static_cast<size_t>(pair) * HIDDEN);
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    float4 d = make_float4(y[0][k].x - y[1][k].x, y[0][k].y - y[1][k].y, y[0][k].z - y[1][k].z,
+                           y[0][k].w - y[1][k].w);
+    if (gamma != nullptr) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * k);
+      d.x *= g.x; d.y *= g.y; d.z *= g.z; d.w *= g.w;
+    }
+    dst[lane + 32 * k] = d;
+  }
+}
+
+}  // namespace vtq
+
+// ================================================================================================
+// C-ABI wrappers
+// ================================================================================================
+using namespace vtq;
+
+extern "C" int vtq_patch_gather(vtq_ctx* ctx, const float* images, int n_img, int H, int W, const double* samples,
+                                int n_set, int n, int patch_offset, int N_total, float* patches_f32,
+                                void* patches_16, int dtype, float* pos, float* scales, int scale_id,
+                                void* stream) {
+  if (!ctx) return VTQ_ERR_INVALID;
+  VTQ_CHECK_ARG(ctx, images && samples, "null pointer");
+  VTQ_CHECK_ARG(ctx, H >= PATCH && W >= PATCH, "image smaller than one patch");
+  VTQ_CHECK_ARG(ctx, n_img >= 1 && n_set >= 1 && n_img % n_set == 0, "n_img must be a multiple of n_set");
+  VTQ_CHECK_ARG(ctx, n >= 0 && patch_offset >= 0 && patch_offset + n <= N_total, "patch range");
+  VTQ_CHECK_ARG(ctx, n_img <= 65535, "n_img <= 65535");
+  VTQ_CHECK_ARG(ctx, dtype == VTQ_F16 || dtype == VTQ_BF16, "dtype");
+  if (n == 0) return VTQ_OK;
+  dim3 grid(n, n_img);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == VTQ_F16)
+    patch_gather_kernel<DT_F16><<<grid, 192, 0, st>>>(images, H, W, samples, n_set, n, patch_offset, N_total,
+                                                      patches_f32, patches_16, pos, scales,
+                                                      static_cast<float>(scale_id));
+  else
+    patch_gather_kernel<DT_BF16><<<grid, 192, 0, st>>>(images, H, W, samples, n_set, n, patch_offset, N_total,
+                                                       patches_f32, patches_16, pos, scales,
+                                                       static_cast<float>(scale_id));
+  VTQ_CHECK_LAUNCH(ctx, "patch_gather launch");
+  return VTQ_OK;
+}
+
+extern "C" int vtq_avgpool2x2(vtq_ctx* ctx, const float* src, float* dst, int planes, int H, int W, void* stream) {
+  if (!ctx) return VTQ_ERR_INVALID;
+  VTQ_CHECK_ARG(ctx, src && dst, "null pointer");
+  VTQ_CHECK_ARG(ctx, planes >= 1 && H >= 2 && W >= 2, "shape");
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t total = static_cast<size_t>(planes) * Ho * Wo;
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (W % 2 == 0 && reinterpret_cast<uintptr_t>(src) % 8 == 0)
+    avgpool2x2_kernel<<<blocks, 256, 0, st>>>(src, dst, H, W, Ho, Wo, total);
+  else
+    avgpool2x2_kernel_unaligned<<<blocks, 256, 0, st>>>(src, dst, H, W, Ho, Wo, total);
+  VTQ_CHECK_LAUNCH(ctx, "avgpool2x2 launch");
+  return VTQ_OK;
+}
+
+extern "C" int vtq_cast_rows(vtq_ctx* ctx, const float* src, void* dst16, int64_t n_elems, int dtype,
+                             void* stream) {
+  if (!ctx) return VTQ_ERR_INVALID;
+  VTQ_CHECK_ARG(ctx, src && dst16, "null pointer");
+  VTQ_CHECK_ARG(ctx, n_elems >= 0 && n_elems % 8 == 0, "element count must be a multiple of 8");
+  VTQ_CHECK_ARG(ctx, (reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst16)) % 16 == 0,
+                "16-byte alignment");
+  VTQ_CHECK_ARG(ctx, dtype == VTQ_F16 || dtype == VTQ_BF16, "dtype");
+  if (n_elems == 0) return VTQ_OK;
+  const size_t n8 = static_cast<size_t>(n_elems) / 8;
+  const unsigned blocks = static_cast<unsigned>((n8 + 255) / 256);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == VTQ_F16) cast_rows_kernel<DT_F16><<<blocks, 256, 0, st>>>(src, dst16, n8);
+  else cast_rows_kernel<DT_BF16><<<blocks, 256, 0, st>>>(src, dst16, n8);
+  VTQ_CHECK_LAUNCH(ctx, "cast_rows launch");
+  return VTQ_OK;
+}
+
+extern "C" int vtq_embed_assemble(vtq_ctx* ctx, const float* proj, const float* pos, const float* scales,
+                                  const float* pos_table, int grid, const float* scale_table, int num_scales,
+                                  const float* cls_token, const float* extra_tokens, int n_extra, int n_seq, int N,
+                                  int hidden, float* x, int32_t* pos_idx, int32_t* scale_idx, void* stream) {
+  if (!ctx) return VTQ_ERR_INVALID;
+  VTQ_CHECK_ARG(ctx, proj && x, "null pointer");
+  VTQ_CHECK_ARG(ctx, hidden % 4 == 0 && hidden >= 4, "hidden must be a multiple of 4");
+  VTQ_CHECK_ARG(ctx, n_seq >= 1 && N >= 1 && n_extra >= 0, "shape");
+  VTQ_CHECK_ARG(ctx, pos_table == nullptr || (pos != nullptr && grid >= 1), "pos table needs uv and a grid width");
+  VTQ_CHECK_ARG(ctx, scale_table == nullptr || (scales != nullptr && num_scales >= 1),
+                "Model uses scale embedding but scales is passed as None.");
+  VTQ_CHECK_ARG(ctx, n_extra == 0 || extra_tokens != nullptr, "extra tokens pointer");
+  const int T = (cls_token ? 1 : 0) + n_extra;
+  const size_t rows = static_cast<size_t>(n_seq) * (T + N);
+  const unsigned blocks = static_cast<unsigned>((rows + 7) / 8);
+  embed_assemble_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      proj, pos, scales, pos_table, grid, scale_table, num_scales, cls_token, extra_tokens, T, n_seq, N, hidden, x,
+      pos_idx, scale_idx);
+  VTQ_CHECK_LAUNCH(ctx, "embed_assemble launch");
+  return VTQ_OK;
+}
+
+extern "C" int vtq_layernorm(vtq_ctx* ctx, const float* x, const float* weight, const float* bias, float eps,
+                             int64_t rows, int hidden, void* out16, int dtype, void* stream) {
+  if (!ctx) return VTQ_ERR_INVALID;
+  VTQ_CHECK_ARG(ctx, x && weight && bias && out16, "null pointer");
+  VTQ_CHECK_ARG(ctx, hidden == 768 || hidden == 1024, "hidden must be 768 or 1024");
+  VTQ_CHECK_ARG(ctx, rows >= 0, "rows");
+  VTQ_CHECK_ARG(ctx, dtype == VTQ_F16 || dtype == VTQ_BF16, "dtype");
+  if (rows == 0) return VTQ_OK;
+  const unsigned blocks = static_cast<unsigned>((rows + 7) / 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t r = static_cast<size_t>(rows);
+  if (hidden == 768) {
+    if (dtype == VTQ_F16) layernorm_kernel<DT_F16, 6><<<blocks, 256, 0, st>>>(x, weight, bias, eps, r, out16);
+    else layernorm_kernel<DT_BF16, 6><<<blocks, 256, 0, st>>>(x, weight, bias, eps, r, out16);
+  } else {
+    if (dtype == VTQ_F16) layernorm_kernel<DT_F16, 8><<<blocks, 256, 0, st>>>(x, weight, bias, eps, r, out16);
+    else layernorm_kernel<DT_BF16, 8><<<blocks, 256, 0, st>>>(x, weight, bias, eps, r, out16);
+  }
+  VTQ_CHECK_LAUNCH(ctx, "layernorm launch");
+  return VTQ_OK;
+}
+
+extern "C" int vtq_cls_diff(vtq_ctx* ctx, const float* x, int B, int S, int hidden, int token,
+                            const float* ln_weight, const float* ln_bias, float eps, const float* gamma,
+                            float* diff, void* stream) {
+  if (!ctx) return VTQ_ERR_INVALID;
+  VTQ_CHECK_ARG(ctx, x && ln_weight && ln_bias && diff, "null pointer");
+  VTQ_CHECK_ARG(ctx, hidden == 768 || hidden == 1024, "hidden must be 768 or 1024");
+  VTQ_CHECK_ARG(ctx, B >= 1 && S >= 1 && token >= 0 && token < S, "shape");
+  const unsigned blocks = static_cast<unsigned>((B + 3) / 4);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (hidden == 768) cls_diff_kernel<6><<<blocks, 128, 0, st>>>(x, B, S, token, ln_weight, ln_bias, eps, gamma, diff);
+  else cls_diff_kernel<8><<<blocks, 128, 0, st>>>(x, B, S, token, ln_weight, ln_bias, eps, gamma, diff);
+  VTQ_CHECK_LAUNCH(ctx, "cls_diff launch");
+  return VTQ_OK;
+}
