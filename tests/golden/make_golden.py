@@ -1,0 +1,133 @@
+"""Generates the committed golden fixtures by running the UNMODIFIED reference (ch-andrei/VTAMIQ at
+/root/reference) on CPU fp32.  Only runs in the build container (the reference does not travel); the
+fixtures it writes are what pins oracle/ on every other machine.
+
+    python tests/golden/make_golden.py
+
+Needs oracle/ref_shims on the path for `timm`, `matplotlib`, `skimage` (absent from the image; none of them
+does inference arithmetic).
+"""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("VTAMIQ_REFERENCE", "/root/reference")
+sys.path[:0] = [os.path.join(ROOT, "oracle", "ref_shims"), REF, os.path.join(ROOT, "tests"), ROOT]
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import synth  # noqa: E402
+from data.patch_sampling import GRID_TYPE_PERTURBED_SIMPLE, PatchSampler, get_iqa_patches  # noqa: E402
+from modules.vtamiq.vtamiq import VTAMIQ  # noqa: E402
+
+torch.set_num_threads(8)
+
+
+def sampler():
+    # train_config.py:284-288
+    return PatchSampler(centerbias_weight=0.0, diff_weight=0.0, uniform_weight=0.1, grid_type=GRID_TYPE_PERTURBED_SIMPLE)
+
+
+def capture_samples(fn):
+    """Run fn while recording what stratified_grid_sampling returned (the coordinates are internal to
+    get_iqa_patches; the device gather needs them as inputs)."""
+    import data.patch_sampling as ps
+    rec = []
+    orig = ps.stratified_grid_sampling
+
+    def spy(*a, **k):
+        out = orig(*a, **k)
+        rec.append(np.array(out, dtype=np.float64, copy=True))
+        return out
+    ps.stratified_grid_sampling = spy
+    try:
+        res = fn()
+    finally:
+        ps.stratified_grid_sampling = orig
+    return res, rec
+
+
+def patches_case(name, H, W, N, n_scales, ratio, seed):
+    ref, dist = synth.make_pair(seed, H, W, 0.1)
+    tens = (synth.to_tensor_normalized(ref), synth.to_tensor_normalized(dist))
+    (patches, pos, scales), rec = capture_samples(lambda: get_iqa_patches(
+        (ref, dist), tens, N, 16, sampler(), n_scales, scale_num_samples_ratio=ratio,
+        use_aligned_patches=True, random_seed=seed))
+    out = dict(ref_u8=ref, dist_u8=dist, N=N, n_scales_requested=n_scales, ratio=ratio,
+               patches=patches.numpy(), pos=pos.numpy())
+    if scales is not None:
+        out["scales"] = scales.numpy()
+    for i, s in enumerate(rec):
+        out[f"samples_{i}"] = s
+    out["n_levels"] = len(rec)
+    np.savez_compressed(os.path.join(HERE, f"patches_{name}.npz"), **out)
+    print("patches", name, patches.shape, [s.shape for s in rec], None if scales is None else np.bincount(scales[0].numpy()))
+
+
+def forward_case(name, vit_cfg, vt_kwargs, B, H, W, N, n_scales, ratio):
+    torch.manual_seed(0)
+    model = VTAMIQ(vit_config=dict(pretrained=False, **vit_cfg), **vt_kwargs).eval()
+    synth.perturb_(model)
+    levels = synth.graded_levels(B)
+    P, POS, SC, U8, SMP = [], [], [], [], []
+    for p in range(B):
+        ref, dist = synth.make_pair(p, H, W, float(levels[p]))
+        tens = (synth.to_tensor_normalized(ref), synth.to_tensor_normalized(dist))
+        (patches, pos, scales), rec = capture_samples(lambda: get_iqa_patches(
+            (ref, dist), tens, N, 16, sampler(), n_scales, scale_num_samples_ratio=ratio,
+            use_aligned_patches=True, random_seed=p))
+        P.append(patches); POS.append(pos); SC.append(scales); U8.append(np.stack([ref, dist])); SMP.append(rec)
+    patches = torch.stack(P)            # (B, 2, N, 3, 16, 16)
+    pos = torch.stack(POS)
+    use_sc = SC[0] is not None
+    scales = torch.stack(SC).to(torch.float32) if use_sc else None   # train.py:254 casts everything to fp32
+    hooks = {}
+    vit = model.transformer
+
+    def keep(tag):
+        def fn(mod, inp, out):
+            hooks.setdefault(tag, []).append((out[0] if isinstance(out, tuple) else out).detach().clone())
+        return fn
+    # Encoder / EncoderLayer are invoked through .forward() (no hooks fire): tap the LayerNorms instead —
+    # the input of layers[1].attention_norm is the residual stream after block 0.
+    def keep_in(tag):
+        def fn(mod, inp):
+            hooks.setdefault(tag, []).append(inp[0].detach().clone())
+        return fn
+    h1 = vit.embeddings.register_forward_hook(keep("embed"))
+    h2 = vit.encoder.layers[1].attention_norm.register_forward_pre_hook(keep_in("layer0"))
+    h3 = vit.encoder.encoder_norm.register_forward_hook(keep("encoded"))
+    h4 = model.diff_scale.register_forward_hook(keep("diff"))
+    with torch.no_grad():
+        q, _ = model((patches[:, 0].clone(), patches[:, 1].clone()), (pos[:, 0].clone(), pos[:, 1].clone()),
+                     (scales[:, 0].clone(), scales[:, 1].clone()) if use_sc else (None, None))
+    for h in (h1, h2, h3, h4):
+        h.remove()
+    out = dict(
+        q=q.numpy(), state_hash=synth.state_hash(model.state_dict()), u8=np.stack(U8), levels=levels,
+        B=B, N=N, n_scales_requested=n_scales, ratio=ratio,
+        vit_cfg=repr(vit_cfg), vt_kwargs=repr(vt_kwargs),
+        # sparse probes of intermediates, ref stream then dist stream: token 0 and the last token
+        embed_tok=np.stack([hooks["embed"][i][:, [0, -1]].numpy() for i in range(2)]),
+        layer0_tok=np.stack([hooks["layer0"][i][:, [0, -1]].numpy() for i in range(2)]),
+        encoded_cls=np.stack([hooks["encoded"][i][:, 0].numpy() for i in range(2)]),
+        diff=hooks["diff"][0].numpy(),
+        n_levels=len(SMP[0]),
+    )
+    for lvl in range(len(SMP[0])):
+        out[f"samples_{lvl}"] = np.stack([SMP[p][lvl] for p in range(B)])   # (B, 2, n_lvl)
+    np.savez_compressed(os.path.join(HERE, f"forward_{name}.npz"), **out)
+    print("forward", name, "q =", q.numpy())
+
+
+if __name__ == "__main__":
+    patches_case("single", 96, 128, 64, 1, 2.0, seed=3)
+    patches_case("multi3", 256, 256, 100, 3, 2.0, seed=4)
+    patches_case("odd2", 250, 301, 80, 2, 1.75, seed=5)
+    patches_case("clamp", 72, 200, 40, 3, 2.0, seed=6)      # image too small for 3 levels: clamped (:398-411)
+    forward_case("default", {}, {}, B=4, H=96, W=128, N=64, n_scales=1, ratio=2.0)
+    forward_case("scales3", dict(num_scales=3), {}, B=2, H=256, W=256, N=100, n_scales=3, ratio=2.0)
+    forward_case("traincfg", dict(num_keep_layers=6, num_extra_tokens=8, use_layer_scale=True),
+                 dict(ca_reduction=16), B=2, H=96, W=128, N=64, n_scales=1, ratio=2.0)

@@ -1,0 +1,173 @@
+"""End-to-end parity of the CUDA path (through the drop-in module -> C-ABI) against the reference's golden
+scores and against the pinned oracle.  Bar (BASELINE.json north_star): |q - q_ref| <= 2e-3 per pair and
+SRCC >= 0.9999 over the batch; gather and embedding indices bit-exact."""
+import ast
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import synth  # noqa: E402
+from oracle import patch_oracle, vtamiq_oracle  # noqa: E402
+
+SCORE_TOL = 2e-3   # north_star tolerance (max-abs per-pair score error)
+SRCC_MIN = 0.9999
+
+
+def _build(vit_cfg, vt_kwargs, **extra):
+    import vtamiq_b200
+    torch.manual_seed(0)
+    m = vtamiq_b200.VTAMIQ(vit_config=dict(pretrained=False, **vit_cfg), **vt_kwargs, **extra).eval()
+    synth.perturb_(m)
+    return m
+
+
+def _srcc(a, b):
+    from scipy.stats import spearmanr
+    return float(spearmanr(a, b)[0])
+
+
+@pytest.mark.parametrize("case", ["default", "scales3", "traincfg"])
+def test_forward_matches_reference_golden(golden_dir, case):
+    g = np.load(os.path.join(golden_dir, f"forward_{case}.npz"))
+    m = _build(ast.literal_eval(str(g["vit_cfg"])), ast.literal_eval(str(g["vt_kwargs"])))
+    assert synth.state_hash(m.state_dict()) == str(g["state_hash"])
+    m = m.cuda()
+    B = int(g["B"])
+    smp = [g[f"samples_{i}"] for i in range(int(g["n_levels"]))]
+    # reference-style inputs (patches from the oracle gather, itself pinned bit-exact to the reference)
+    P, POS, SC = [], [], []
+    for b in range(B):
+        tens = np.stack([synth.to_tensor_normalized(g["u8"][b, k]).numpy() for k in range(2)])
+        p, pos, sc = patch_oracle.extract_patches(tens, [s[b] for s in smp])
+        P.append(p); POS.append(pos); SC.append(sc)
+    P, POS = torch.from_numpy(np.stack(P)).cuda(), torch.from_numpy(np.stack(POS)).cuda()
+    use_sc = SC[0] is not None
+    SCt = torch.from_numpy(np.stack(SC)).float().cuda() if use_sc else None
+    with torch.no_grad():
+        q, none = m((P[:, 0].contiguous(), P[:, 1].contiguous()), (POS[:, 0].contiguous(), POS[:, 1].contiguous()),
+                    (SCt[:, 0].contiguous(), SCt[:, 1].contiguous()) if use_sc else (None, None))
+    assert none is None and q.shape == (B,) and q.dtype == torch.float32
+    err = np.abs(q.cpu().numpy() - g["q"]).max()
+    assert err <= SCORE_TOL, (err, q.cpu().numpy(), g["q"])
+    # fast entry: device gather + forward, same scores
+    images = torch.stack([torch.stack([synth.to_tensor_normalized(g["u8"][b, k]) for b in range(B)]) for k in range(2)]).cuda()
+    samples = [torch.from_numpy(s).cuda() for s in smp]
+    with torch.no_grad():
+        q2 = m.forward_from_images(images, samples)
+    assert np.abs(q2.cpu().numpy() - g["q"]).max() <= SCORE_TOL
+    assert torch.allclose(q, q2, atol=1e-6)
+
+
+def test_intermediates_and_indices_default(golden_dir):
+    """Residual stream after embedding / block 0 / the final CLS, against the reference's probes."""
+    g = np.load(os.path.join(golden_dir, "forward_default.npz"))
+    m = _build({}, {}, cuda_graph=False).cuda()
+    B, N = int(g["B"]), int(g["N"])
+    images = torch.stack([torch.stack([synth.to_tensor_normalized(g["u8"][b, k]) for b in range(B)]) for k in range(2)]).cuda()
+    samples = [torch.from_numpy(g["samples_0"]).cuda()]
+    eng = m.engine
+    eng.dump_indices = True
+    with torch.no_grad():
+        q = m.forward_from_images(images, samples)
+    ws = eng.workspace(B, N)
+    # indices: bit-exact vs the reference formula on the reference's uv
+    pos = ws.pos.cpu().numpy()
+    assert np.array_equal(ws.pos_idx.cpu().numpy().astype(np.int64), patch_oracle.pos_index(pos, 24))
+    # only one layer deep is checked tightly (operand rounding accumulates with depth)
+    eng.dump_indices = False
+    assert np.abs(q.cpu().numpy() - g["q"]).max() <= SCORE_TOL
+    diff = ws.diff.cpu().numpy()
+    assert np.abs(diff - g["diff"]).max() < 2e-2   # fp16 operands through 12 blocks; the score bar is the gate
+
+
+@pytest.mark.parametrize("N,B", [(256, 32), (500, 32)])
+def test_forward_parity_batch32_vs_oracle(N, B):
+    """BASELINE configs 1/2 shape (384x512, single scale): max-abs 2e-3 and SRCC >= 0.9999 over the batch."""
+    H, W = 384, 512
+    m = _build({}, {})
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m = m.cuda()
+    levels = synth.graded_levels(B)
+    rng = np.random.default_rng(123)
+    imgs, smp = [], []
+    for p in range(B):
+        ref, dist = synth.make_pair(p, H, W, float(levels[p]))
+        imgs.append(torch.stack([synth.to_tensor_normalized(ref), synth.to_tensor_normalized(dist)]))
+        smp.append(synth.jittered_samples(rng, H, W, N))
+    images = torch.stack(imgs, dim=1).contiguous()          # (2, B, 3, H, W)
+    samples = np.stack(smp)                                 # (B, 2, N)
+    with torch.no_grad():
+        q_gpu = m.forward_from_images(images.cuda(), [torch.from_numpy(samples).cuda()]).cpu().numpy()
+    # oracle on the same patch sets
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    P, POS = [], []
+    for p in range(B):
+        pp, pos, _ = patch_oracle.extract_patches(images[:, p].numpy(), [samples[p]])
+        P.append(pp); POS.append(pos)
+    P, POS = torch.from_numpy(np.stack(P)), torch.from_numpy(np.stack(POS))
+    q_ref = vtamiq_oracle.vtamiq_forward(sd, (P[:, 0], P[:, 1]), (POS[:, 0], POS[:, 1]), None).numpy()
+    err = np.abs(q_gpu - q_ref).max()
+    gap = np.diff(np.sort(q_ref)).min()
+    srcc = _srcc(q_gpu, q_ref)
+    print(f"N={N} B={B} max|dq|={err:.2e} srcc={srcc:.6f} min score gap={gap:.2e} spread={q_ref.std():.3f}")
+    assert err <= SCORE_TOL, err
+    assert srcc >= SRCC_MIN, (srcc, gap)
+
+
+def test_bf16_operands_documented_gap():
+    """bf16 operands run (same tcgen05 path) but are NOT the parity configuration: SURVEY §7.3 measured 3.2e-3."""
+    B, N, H, W = 8, 256, 384, 512
+    m16 = _build({}, {}).cuda()
+    mbf = _build({}, {}, operand_dtype="bf16").cuda()
+    levels = synth.graded_levels(B)
+    rng = np.random.default_rng(5)
+    imgs, smp = [], []
+    for p in range(B):
+        ref, dist = synth.make_pair(p, H, W, float(levels[p]))
+        imgs.append(torch.stack([synth.to_tensor_normalized(ref), synth.to_tensor_normalized(dist)]))
+        smp.append(synth.jittered_samples(rng, H, W, N))
+    images = torch.stack(imgs, dim=1).contiguous().cuda()
+    samples = [torch.from_numpy(np.stack(smp)).cuda()]
+    with torch.no_grad():
+        a = m16.forward_from_images(images, samples).cpu().numpy()
+        b = mbf.forward_from_images(images, samples).cpu().numpy()
+    assert np.isfinite(b).all()
+    assert np.abs(a - b).max() < 2e-2
+
+
+def test_state_change_invalidates_packed_weights():
+    m = _build({}, {}, cuda_graph=True).cuda()
+    B, N = 2, 64
+    g = torch.Generator(device="cuda").manual_seed(0)
+    p = (torch.randn(B, N, 3, 16, 16, device="cuda", generator=g), torch.randn(B, N, 3, 16, 16, device="cuda", generator=g))
+    pos = (torch.rand(B, N, 2, device="cuda", generator=g),) * 2
+    with torch.no_grad():
+        q1, _ = m(p, pos, (None, None))
+        q1b, _ = m(p, pos, (None, None))
+        assert torch.equal(q1, q1b)                      # graph replay is deterministic
+        m.q_predictor[4].bias.add_(1.0)                  # in-place edit bumps the version counter
+        q2, _ = m(p, pos, (None, None))
+        assert torch.allclose(q2, q1 + 1.0, atol=1e-5)
+        sd = {k: v.clone() for k, v in m.state_dict().items()}
+        sd["q_predictor.4.bias"] = sd["q_predictor.4.bias"] - 1.0
+        m.load_state_dict(sd, strict=True)
+        q3, _ = m(p, pos, (None, None))
+        assert torch.allclose(q3, q1, atol=1e-5)
+
+
+def test_inputs_are_not_mutated_and_training_mode_raises():
+    m = _build({}, {}).cuda()
+    B, N = 1, 32
+    p = torch.randn(B, N, 3, 16, 16, device="cuda")
+    pos = torch.rand(B, N, 2, device="cuda")
+    p0, pos0 = p.clone(), pos.clone()
+    with torch.no_grad():
+        m((p, p), (pos, pos), (None, None))
+    assert torch.equal(p, p0) and torch.equal(pos, pos0)
+    m.train()
+    with pytest.raises(RuntimeError, match="inference path only"):
+        m((p, p), (pos, pos), (None, None))

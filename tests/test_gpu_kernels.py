@@ -1,0 +1,266 @@
+"""Per-kernel parity on a real B200, through the C-ABI (ctypes), against torch fp32 math / the oracle."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import synth  # noqa: E402
+from oracle import patch_oracle, vtamiq_oracle  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from vtamiq_b200 import _lib
+    assert torch.cuda.is_available(), "these tests need the GPU box"
+    return _lib.get_context(0)
+
+
+def P(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def ST():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+DT = {"fp16": (0, torch.float16), "bf16": (1, torch.bfloat16)}
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("dt", ["fp16", "bf16"])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 768, 768), (1000, 2304, 768), (257, 3072, 768),
+                                   (515, 768, 3072), (32064, 768, 768)])
+def test_gemm_bias_h(ctx, dt, M, N, K):
+    code, tdt = DT[dt]
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).to(tdt)
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(tdt)
+    b = torch.randn(N, device="cuda", generator=g)
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=tdt)
+    ctx.call("vtq_gemm", P(A), 0, P(W), P(b), M, N, K, code, 0, P(out), 0, None, ST())
+    torch.cuda.synchronize()
+    want = A.float() @ W.float().t() + b
+    err = (out.float() - want).abs().max().item()
+    tol = 2e-2 if dt == "bf16" else 4e-3
+    assert torch.isfinite(out.float()).all()
+    assert err < tol, err
+
+
+@pytest.mark.parametrize("dt", ["fp16"])
+def test_gemm_gelu(ctx, dt):
+    code, tdt = DT[dt]
+    M, N, K = 700, 3072, 768
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.randn(M, K, device="cuda", generator=g).to(tdt)
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(tdt)
+    b = torch.randn(N, device="cuda", generator=g)
+    out = torch.empty(M, N, device="cuda", dtype=tdt)
+    ctx.call("vtq_gemm", P(A), 0, P(W), P(b), M, N, K, code, 1, P(out), 0, None, ST())
+    torch.cuda.synchronize()
+    want = torch.nn.functional.gelu(A.float() @ W.float().t() + b)
+    assert (out.float() - want).abs().max().item() < 4e-3
+
+
+@pytest.mark.parametrize("M,N,K,use_gamma", [(300, 768, 768, False), (1000, 768, 3072, True), (64, 768, 768, True)])
+def test_gemm_f32_store_and_residual(ctx, M, N, K, use_gamma):
+    g = torch.Generator(device="cuda").manual_seed(11)
+    A = torch.randn(M, K, device="cuda", generator=g).half()
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).half()
+    b = torch.randn(N, device="cuda", generator=g)
+    gamma = torch.rand(N, device="cuda", generator=g) + 0.5 if use_gamma else None
+    base = A.float() @ W.float().t() + b
+    out = torch.full((M, N), float("nan"), device="cuda")
+    ctx.call("vtq_gemm", P(A), 0, P(W), P(b), M, N, K, 0, 2, P(out), 0, None, ST())
+    torch.cuda.synchronize()
+    assert (out - base).abs().max().item() < 2e-3
+    x0 = torch.randn(M, N, device="cuda", generator=g)
+    x = x0.clone()
+    ctx.call("vtq_gemm", P(A), 0, P(W), P(b), M, N, K, 0, 3, P(x), 0, P(gamma), ST())
+    torch.cuda.synchronize()
+    want = x0 + (base * gamma if use_gamma else base)
+    assert (x - want).abs().max().item() < 2e-3
+
+
+def test_gemm_rejects_bad_shapes(ctx):
+    from vtamiq_b200._lib import VtqError
+    A = torch.zeros(128, 100, device="cuda", dtype=torch.float16)
+    W = torch.zeros(128, 100, device="cuda", dtype=torch.float16)
+    b = torch.zeros(128, device="cuda")
+    o = torch.zeros(128, 128, device="cuda", dtype=torch.float16)
+    with pytest.raises(VtqError, match="multiple of 64"):
+        ctx.call("vtq_gemm", P(A), 0, P(W), P(b), 128, 128, 100, 0, 0, P(o), 0, None, ST())
+
+
+# ------------------------------------------------------------------------------------------ attention
+def _attn_ref(qkv, n_seq, S, heads):
+    H = heads * 64
+    x = qkv.float().view(n_seq, S, 3, heads, 64)
+    q, k, v = x[:, :, 0].permute(0, 2, 1, 3), x[:, :, 1].permute(0, 2, 1, 3), x[:, :, 2].permute(0, 2, 1, 3)
+    p = torch.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1)
+    return (p @ v).permute(0, 2, 1, 3).reshape(n_seq * S, H)
+
+
+@pytest.mark.parametrize("dt", ["fp16", "bf16"])
+@pytest.mark.parametrize("n_seq,S,heads", [(2, 128, 2), (3, 65, 12), (2, 129, 12), (4, 501, 12), (2, 257, 12),
+                                           (1, 1, 12), (1, 1300, 4)])
+def test_attention(ctx, dt, n_seq, S, heads):
+    code, tdt = DT[dt]
+    H = heads * 64
+    g = torch.Generator(device="cuda").manual_seed(S)
+    qkv = (torch.randn(n_seq * S, 3 * H, device="cuda", generator=g) * 1.5).to(tdt)
+    out = torch.full((n_seq * S, H), float("nan"), device="cuda", dtype=tdt)
+    ctx.call("vtq_attention_fwd", P(qkv), P(out), n_seq, S, heads, code, ST())
+    torch.cuda.synchronize()
+    want = _attn_ref(qkv, n_seq, S, heads)
+    assert torch.isfinite(out.float()).all()
+    err = (out.float() - want).abs().max().item()
+    assert err < (3e-2 if dt == "bf16" else 4e-3), err
+
+
+# ------------------------------------------------------------------------------------------ row-wise kernels
+@pytest.mark.parametrize("dt", ["fp16", "bf16"])
+@pytest.mark.parametrize("rows", [1, 7, 1003])
+def test_layernorm(ctx, dt, rows):
+    code, tdt = DT[dt]
+    g = torch.Generator(device="cuda").manual_seed(rows)
+    x = torch.randn(rows, 768, device="cuda", generator=g) * 3 + 0.7
+    w = torch.randn(768, device="cuda", generator=g)
+    b = torch.randn(768, device="cuda", generator=g)
+    out = torch.empty(rows, 768, device="cuda", dtype=tdt)
+    ctx.call("vtq_layernorm", P(x), P(w), P(b), 1e-6, rows, 768, P(out), code, ST())
+    torch.cuda.synchronize()
+    want = torch.nn.functional.layer_norm(x, (768,), w, b, 1e-6)
+    # identical up to the final 16-bit rounding
+    assert (out.float() - want.to(tdt).float()).abs().max().item() <= (0.04 if dt == "bf16" else 0.005)
+    assert (out.float() - want).abs().max().item() < (0.05 if dt == "bf16" else 0.006)
+
+
+def test_cast_rows(ctx):
+    x = torch.randn(5, 768, device="cuda")
+    for name, (code, tdt) in DT.items():
+        out = torch.empty(5, 768, device="cuda", dtype=tdt)
+        ctx.call("vtq_cast_rows", P(x), P(out), x.numel(), code, ST())
+        torch.cuda.synchronize()
+        assert torch.equal(out, x.to(tdt))
+
+
+@pytest.mark.parametrize("n_extra,use_scales", [(0, False), (8, True)])
+def test_embed_assemble_indices_bit_exact(ctx, n_extra, use_scales):
+    n_seq, N, H = 3, 77, 768
+    g = torch.Generator(device="cuda").manual_seed(3)
+    proj = torch.randn(n_seq * N, H, device="cuda", generator=g)
+    pos = torch.rand(n_seq * N, 2, device="cuda", generator=g)
+    pos[0] = torch.tensor([0.0, 0.0]); pos[1] = torch.tensor([0.99999899, 0.99999899]); pos[2] = torch.tensor([1 / 24, 23 / 24])
+    scales = torch.randint(0, 5, (n_seq * N,), device="cuda", generator=g).float() if use_scales else None
+    pos_table = torch.randn(577, H, device="cuda", generator=g)
+    scale_table = torch.randn(4, H, device="cuda", generator=g) if use_scales else None
+    cls = torch.randn(H, device="cuda", generator=g)
+    extra = torch.randn(n_extra, H, device="cuda", generator=g) if n_extra else None
+    T = 1 + n_extra
+    x = torch.full((n_seq, T + N, H), float("nan"), device="cuda")
+    pidx = torch.zeros(n_seq * N, dtype=torch.int32, device="cuda")
+    sidx = torch.zeros(n_seq * N, dtype=torch.int32, device="cuda")
+    ctx.call("vtq_embed_assemble", P(proj), P(pos), P(scales), P(pos_table), 24, P(scale_table), 3 if use_scales else 0,
+             P(cls), P(extra), n_extra, n_seq, N, H, P(x), P(pidx), P(sidx), ST())
+    torch.cuda.synchronize()
+    want_idx = patch_oracle.pos_index(pos.cpu().numpy(), 24)
+    assert np.array_equal(pidx.cpu().numpy().astype(np.int64), want_idx)
+    want = proj + pos_table[torch.from_numpy(want_idx).cuda()]
+    if use_scales:
+        want_s = patch_oracle.scale_index(scales.cpu().numpy(), 3)
+        assert np.array_equal(sidx.cpu().numpy().astype(np.int64), want_s)
+        want = want + scale_table[torch.from_numpy(want_s).cuda()]
+    assert torch.equal(x[:, T:].reshape(-1, H), want)          # fp32 adds in the reference's order: bit-exact
+    assert torch.equal(x[:, 0], (cls + pos_table[0]).expand(n_seq, H))
+    if n_extra:
+        assert torch.equal(x[:, 1:T], extra.expand(n_seq, n_extra, H))
+
+
+def test_embed_requires_scales(ctx):
+    from vtamiq_b200._lib import VtqError
+    t = torch.zeros(8, 768, device="cuda")
+    with pytest.raises(VtqError, match="scales is passed as None"):
+        ctx.call("vtq_embed_assemble", P(t), P(t), None, P(t), 24, P(t), 3, P(t), None, 0, 1, 8, 768, P(t), None, None, ST())
+
+
+def test_cls_diff(ctx):
+    B, S, H = 5, 9, 768
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.randn(2 * B, S, H, device="cuda", generator=g) * 2
+    w = torch.randn(H, device="cuda", generator=g); b = torch.randn(H, device="cuda", generator=g)
+    gamma = torch.rand(H, device="cuda", generator=g) + 0.5
+    out = torch.empty(B, H, device="cuda")
+    ctx.call("vtq_cls_diff", P(x), B, S, H, 0, P(w), P(b), 1e-6, P(gamma), P(out), ST())
+    torch.cuda.synchronize()
+    ln = torch.nn.functional.layer_norm(x[:, 0].cpu(), (H,), w.cpu(), b.cpu(), 1e-6)
+    want = (ln[:B] - ln[B:]) * gamma.cpu()
+    assert (out.cpu() - want).abs().max().item() < 5e-6
+
+
+@pytest.mark.parametrize("B", [1, 5, 33])
+def test_diffnet_head_matches_oracle(ctx, B):
+    import vtamiq_b200
+    torch.manual_seed(0)
+    m = vtamiq_b200.VTAMIQ(vit_config=dict(pretrained=False, num_keep_layers=1)).eval()
+    synth.perturb_(m)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m = m.cuda()
+    eng = m.engine
+    eng._ensure_ready()
+    d = torch.randn(B, 768, generator=torch.Generator().manual_seed(B)) * 0.5
+    want = vtamiq_oracle.diffnet_head(sd, vtamiq_oracle._cfg_from_state(sd), d)
+    dd = d.cuda()
+    q = torch.empty(B, device="cuda")
+    ws = torch.empty(ctx.workspace_bytes(B, 768), dtype=torch.uint8, device="cuda")
+    ctx.call("vtq_diffnet_head", P(dd), eng._tail_params, len(eng._tail_params), eng.num_rgs, eng.num_rcabs, 768,
+             eng.ca_hidden, eng.head_hidden, B, P(q), P(ws), ST())
+    torch.cuda.synchronize()
+    assert (q.cpu() - want).abs().max().item() < 2e-5
+
+
+# ------------------------------------------------------------------------------------------ patch gather
+@pytest.mark.parametrize("case", ["single", "multi3", "odd2", "clamp"])
+def test_patch_gather_bit_exact_vs_reference_golden(golden_dir, case):
+    from vtamiq_b200 import extract_patches
+    g = np.load(os.path.join(golden_dir, f"patches_{case}.npz"))
+    tens = torch.stack([synth.to_tensor_normalized(g["ref_u8"]), synth.to_tensor_normalized(g["dist_u8"])]).cuda()
+    smp = [g[f"samples_{i}"] for i in range(int(g["n_levels"]))]
+    patches, pos, scales = extract_patches(tens, smp)
+    torch.cuda.synchronize()
+    assert np.array_equal(patches.cpu().numpy().view(np.uint32), g["patches"].view(np.uint32))
+    assert np.array_equal(pos.cpu().numpy().view(np.uint32), g["pos"].view(np.uint32))
+    if "scales" in g.files:
+        assert scales.dtype == torch.int32 and np.array_equal(scales.cpu().numpy(), g["scales"])
+    else:
+        assert scales is None
+
+
+def test_patch_gather_full_size_vs_oracle():
+    """cfg3-like: 1024x1024, 3 levels, 500 patches (380/96/24) — bit-exact against the numpy oracle."""
+    from vtamiq_b200 import extract_patches
+    rng = np.random.default_rng(7)
+    tens = rng.standard_normal((2, 3, 1024, 1024)).astype(np.float32)
+    smp = [synth.jittered_samples(rng, 1024 >> s, 1024 >> s, n) for s, n in enumerate((380, 96, 24))]
+    smp[0][:, 0] = [0.0, 0.0]; smp[0][:, 1] = [1008.0, 1008.0]; smp[0][:, 2] = [1007.999999, 0.5]   # edges
+    want_p, want_pos, want_s = patch_oracle.extract_patches(tens, smp)
+    patches, pos, scales = extract_patches(torch.from_numpy(tens).cuda(), smp)
+    torch.cuda.synchronize()
+    assert np.array_equal(patches.cpu().numpy().view(np.uint32), want_p.view(np.uint32))
+    assert np.array_equal(pos.cpu().numpy().view(np.uint32), want_pos.view(np.uint32))
+    assert np.array_equal(scales.cpu().numpy(), want_s)
+
+
+def test_avgpool_bit_exact(ctx):
+    x = torch.randn(5, 37, 50, device="cuda")
+    out = torch.empty(5, 18, 25, device="cuda")
+    ctx.call("vtq_avgpool2x2", P(x), P(out), 5, 37, 50, ST())
+    y = torch.randn(4, 21, 33, device="cuda")       # odd width -> scalar-load variant
+    out2 = torch.empty(4, 10, 16, device="cuda")
+    ctx.call("vtq_avgpool2x2", P(y), P(out2), 4, 21, 33, ST())
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), patch_oracle.avgpool2x2(x.cpu().numpy()).view(np.uint32))
+    assert np.array_equal(out2.cpu().numpy().view(np.uint32), patch_oracle.avgpool2x2(y.cpu().numpy()).view(np.uint32))

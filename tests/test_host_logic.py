@@ -1,0 +1,174 @@
+"""Host-side logic: per-scale patch budgets, scale clamp, module contract (state_dict, npz loader), sharding."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import vtamiq_b200
+from vtamiq_b200 import patch_sampling as ps
+from vtamiq_b200.parallel import shard_pairs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_patches_per_scale_known_values():
+    # probes of the reference's compute_num_patches_per_scale
+    assert ps.compute_num_patches_per_scale(500, 3, 2.0)[::-1].tolist() == [380, 96, 24]
+    assert ps.compute_num_patches_per_scale(500, 3, 1.75)[::-1].tolist() == [360, 108, 32]
+    assert ps.compute_num_patches_per_scale(100, 3, 2.0)[::-1].tolist() == [75, 20, 5]   # golden multi3
+    assert ps.compute_num_patches_per_scale(80, 2, 1.75)[::-1].tolist() == [61, 19]      # golden odd2
+    assert ps.compute_num_patches_per_scale(256, 1, 2.0).tolist() == [256]
+    for n in (3, 7, 500, 5000):
+        for k in (1, 2, 3, 4):
+            if n >= k:
+                assert ps.compute_num_patches_per_scale(n, k, 1.7).sum() == n
+
+
+def test_scale_clamp_by_image_size():
+    assert ps.compute_patch_num_scales(1, 384, 512, 16, 16) == 1
+    assert ps.compute_patch_num_scales(3, 1024, 1024, 16, 16) == 3
+    assert ps.compute_patch_num_scales(3, 256, 256, 16, 16) == 3
+    assert ps.compute_patch_num_scales(3, 72, 200, 16, 16) == 2      # golden "clamp" case: 2 levels
+    assert ps.compute_patch_num_scales(5, 40, 40, 16, 16) == 1
+
+
+def test_shard_pairs_partition():
+    for n in (0, 1, 7, 32, 2048):
+        for w in (1, 2, 3, 8):
+            spans = [shard_pairs(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_pairs(4, 2, 2)
+
+
+@pytest.fixture(scope="module")
+def model():
+    torch.manual_seed(0)
+    return vtamiq_b200.VTAMIQ(vit_config=dict(pretrained=False)).eval()
+
+
+def test_state_dict_layout(model):
+    sd = model.state_dict()
+    assert len(sd) == 326 and sum(v.numel() for v in sd.values()) == 101014674   # SURVEY §8b probe
+    shapes = {
+        "transformer.embeddings.cls_token": (1, 1, 768),
+        "transformer.embeddings.patch_embeddings.weight": (768, 3, 16, 16),
+        "transformer.embeddings.positional_embeddings.positional_embeddings": (1, 577, 768),
+        "transformer.encoder.encoder_norm.weight": (768,),
+        "transformer.encoder.layers.11.attn.query.weight": (768, 768),
+        "transformer.encoder.layers.0.ffn.fc1.weight": (3072, 768),
+        "transformer.encoder.layers.0.ffn.fc2.weight": (768, 3072),
+        "diff_scale.gamma": (768,),
+        "quality_decoder.0.body.0.body.1.weight": (1,),
+        "quality_decoder.3.body.3.body.2.weight": (768, 768, 1),
+        "quality_decoder.0.body.0.body.4.conv_du.1.weight": (96, 768, 1),
+        "quality_decoder.0.body.0.body.4.conv_du.4.weight": (768, 96, 1),
+        "quality_decoder.2.body.4.weight": (768, 768, 1),
+        "quality_decoder.4.bias": (768,),
+        "q_predictor.1.weight": (192, 768),
+        "q_predictor.2.weight": (1,),
+        "q_predictor.4.weight": (1, 192),
+    }
+    for k, s in shapes.items():
+        assert tuple(sd[k].shape) == s, k
+    assert len(model.transformer.encoder.layers) == 12 and model.vit_num_layers == 12
+    assert "_engine" not in "".join(sd.keys())
+
+
+def test_traincfg_variant_keys():
+    torch.manual_seed(0)
+    m = vtamiq_b200.VTAMIQ(vit_config=dict(pretrained=False, num_keep_layers=6, num_extra_tokens=8,
+                                           use_layer_scale=True, num_scales=3), ca_reduction=16)
+    sd = m.state_dict()
+    assert tuple(sd["transformer.embeddings.extra_tokens"].shape) == (1, 8, 768)
+    assert tuple(sd["transformer.embeddings.scale_embeddings.scale_embeddings"].shape) == (1, 4, 768)
+    assert tuple(sd["transformer.encoder.layers.5.ls2.gamma"].shape) == (768,)
+    assert "transformer.encoder.layers.6.ls1.gamma" not in sd
+    assert tuple(sd["quality_decoder.1.body.2.body.4.conv_du.1.weight"].shape) == (48, 768, 1)
+    m2 = vtamiq_b200.VTAMIQ(vit_config=dict(pretrained=False, num_keep_layers=6, num_extra_tokens=8,
+                                            use_layer_scale=True, num_scales=3), ca_reduction=16)
+    m2.load_state_dict(sd, strict=True)
+
+
+def test_set_freeze_state(model):
+    fd = dict(freeze_dict_vit=dict(freeze_encoder=True, freeze_encoder_adapters=False, freeze_encoder_layerscale=False,
+                                   freeze_embeddings_cls_token=True, freeze_embeddings_extra_tokens=True,
+                                   freeze_embeddings_patch=True, freeze_embeddings_pos=True,
+                                   freeze_embeddings_scale=True),
+              freeze_quality_decoder=False, freeze_q_predictor=False)
+    model.set_freeze_state(True, fd)
+    assert not model.transformer.encoder.layers[0].attn.query.weight.requires_grad
+    assert not model.transformer.embeddings.cls_token.requires_grad
+    assert model.q_predictor[1].weight.requires_grad
+    model.set_freeze_state(False, fd)
+    assert model.transformer.encoder.layers[0].attn.query.weight.requires_grad
+
+
+def test_npz_loader_layout(model, tmp_path):
+    """Synthetic JAX-format checkpoint -> torch layout rules of transformer.py:287-325,:643-668."""
+    rng = np.random.default_rng(0)
+    H, M = 768, 3072
+    w = {"embedding/kernel": rng.standard_normal((16, 16, 3, H), dtype=np.float32),
+         "embedding/bias": rng.standard_normal(H, dtype=np.float32),
+         "cls": rng.standard_normal((1, 1, H), dtype=np.float32),
+         "Transformer/posembed_input/pos_embedding": rng.standard_normal((1, 577, H), dtype=np.float32),
+         "Transformer/encoder_norm/scale": rng.standard_normal(H, dtype=np.float32),
+         "Transformer/encoder_norm/bias": rng.standard_normal(H, dtype=np.float32)}
+    for i in range(12):
+        r = f"Transformer/encoderblock_{i}/"
+        for n in ("query", "key", "value"):
+            w[r + f"MultiHeadDotProductAttention_1/{n}/kernel"] = rng.standard_normal((H, 12, 64), dtype=np.float32)
+            w[r + f"MultiHeadDotProductAttention_1/{n}/bias"] = rng.standard_normal((12, 64), dtype=np.float32)
+        w[r + "MultiHeadDotProductAttention_1/out/kernel"] = rng.standard_normal((12, 64, H), dtype=np.float32)
+        w[r + "MultiHeadDotProductAttention_1/out/bias"] = rng.standard_normal(H, dtype=np.float32)
+        w[r + "MlpBlock_3/Dense_0/kernel"] = rng.standard_normal((H, M), dtype=np.float32)
+        w[r + "MlpBlock_3/Dense_0/bias"] = rng.standard_normal(M, dtype=np.float32)
+        w[r + "MlpBlock_3/Dense_1/kernel"] = rng.standard_normal((M, H), dtype=np.float32)
+        w[r + "MlpBlock_3/Dense_1/bias"] = rng.standard_normal(H, dtype=np.float32)
+        for n in ("LayerNorm_0", "LayerNorm_2"):
+            w[r + n + "/scale"] = rng.standard_normal(H, dtype=np.float32)
+            w[r + n + "/bias"] = rng.standard_normal(H, dtype=np.float32)
+    path = tmp_path / "vit.npz"
+    np.savez(path, **w)
+    model.transformer.load_from(np.load(path))
+    sd = model.state_dict()
+    L = "transformer.encoder.layers.7."
+    r = "Transformer/encoderblock_7/"
+    eq = lambda a, b: np.array_equal(a.numpy(), b)
+    assert eq(sd[L + "attn.query.weight"], w[r + "MultiHeadDotProductAttention_1/query/kernel"].reshape(H, H).T)
+    assert eq(sd[L + "attn.out.weight"], w[r + "MultiHeadDotProductAttention_1/out/kernel"].reshape(H, H).T)
+    assert eq(sd[L + "attn.key.bias"], w[r + "MultiHeadDotProductAttention_1/key/bias"].reshape(-1))
+    assert eq(sd[L + "ffn.fc1.weight"], w[r + "MlpBlock_3/Dense_0/kernel"].T)
+    assert eq(sd[L + "ffn.fc2.weight"], w[r + "MlpBlock_3/Dense_1/kernel"].T)
+    assert eq(sd[L + "ffn_norm.weight"], w[r + "LayerNorm_2/scale"])
+    assert eq(sd["transformer.embeddings.patch_embeddings.weight"], w["embedding/kernel"].transpose(3, 2, 0, 1))
+    assert eq(sd["transformer.embeddings.positional_embeddings.positional_embeddings"],
+              w["Transformer/posembed_input/pos_embedding"])
+    assert eq(sd["transformer.embeddings.cls_token"], w["cls"])
+
+
+def test_forward_without_gpu_raises(model):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    B, N = 1, 8
+    p = torch.zeros(B, N, 3, 16, 16)
+    pos = torch.zeros(B, N, 2)
+    with torch.no_grad(), pytest.raises(Exception, match="CUDA|CPU"):
+        model((p, p), (pos, pos), (None, None))
+
+
+def test_gather_scores_gloo_world2():
+    """N>1 path on CPU: two gloo ranks shard 7 pairs (ragged 4+3) and all-gather the scores in pair order."""
+    script = os.path.join(ROOT, "tests", "_dist_worker.py")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", script],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("DIST_OK") == 2, out.stdout + out.stderr

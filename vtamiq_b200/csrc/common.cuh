@@ -58,7 +58,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 // Bounded spin: a protocol bug must surface as a trapped launch, never as a hung GPU.
 #ifndef VTQ_SPIN_LIMIT
-#define VTQ_SPIN_LIMIT (1u << 27)
+#define VTQ_SPIN_LIMIT (1u << 22)
 #endif
 
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {

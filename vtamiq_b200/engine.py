@@ -1,0 +1,286 @@
+"""Host-side orchestration of the sm_100a kernels for one VTAMIQ forward.
+
+PyTorch is used here for device memory, streams and CUDA-graph capture only; every arithmetic step
+of the path is a call into libvtamiq_b200.so (see include/vtamiq_b200.h).  The call sequence
+restates reference ``VTAMIQ.forward`` (modules/vtamiq/vtamiq.py:94-119) →
+``VisionTransformer.forward`` (modules/VisionTransformer/transformer.py:628-641) →
+``Embeddings.forward`` (:526-562) → 12 × ``EncoderLayer.forward`` (:275-285) → ``encoder_norm``
+(:376) → DiffNet + head, with ref and dist stacked into ONE pass of 2B sequences.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from ._lib import (EPI_BIAS_F32, EPI_BIAS_GELU_H, EPI_BIAS_H, EPI_BIAS_RESID_F32, VTQ_BF16, VTQ_F16,
+                   VtqError, get_context)
+
+_DTYPES = {"fp16": (VTQ_F16, torch.float16), "bf16": (VTQ_BF16, torch.bfloat16)}
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+@dataclass
+class _LayerPack:
+    ln1_w: torch.Tensor
+    ln1_b: torch.Tensor
+    w_qkv: torch.Tensor
+    b_qkv: torch.Tensor
+    w_o: torch.Tensor
+    b_o: torch.Tensor
+    g1: torch.Tensor | None
+    ln2_w: torch.Tensor
+    ln2_b: torch.Tensor
+    w_fc1: torch.Tensor
+    b_fc1: torch.Tensor
+    w_fc2: torch.Tensor
+    b_fc2: torch.Tensor
+    g2: torch.Tensor | None
+
+
+class _Workspace:
+    """Device buffers for one (B, N) problem; allocated once, reused by every forward / graph replay."""
+
+    def __init__(self, eng: "Engine", B: int, N: int):
+        dev, t16 = eng.device, eng.torch16
+        H, Mlp, T = eng.hidden, eng.mlp_dim, eng.num_tokens
+        self.B, self.N, self.S = B, N, T + N
+        n_seq = 2 * B
+        rows, prow = n_seq * self.S, n_seq * N
+        e = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt, device=dev)
+        self.patches16 = e(prow, eng.patch_elems, dt=t16)
+        self.proj = e(prow, H)
+        self.pos = e(prow, 2)
+        self.scales = e(prow)
+        self.x = e(rows, H)
+        self.ln = e(rows, H, dt=t16)
+        self.qkv = e(rows, 3 * H, dt=t16)
+        self.att = e(rows, H, dt=t16)
+        self.h1 = e(rows, Mlp, dt=t16)
+        self.diff = e(B, H)
+        self.q = e(B)
+        self.tail_ws = torch.empty(max(eng.ctx.workspace_bytes(B, H), 16), dtype=torch.uint8, device=dev)
+        self.pos_idx = None    # optional int32 dumps for the parity tests
+        self.scale_idx = None
+        self.graph = None      # captured encoder+tail graph
+
+
+class Engine:
+    """Packed weights + workspaces + launch sequence for one VTAMIQ module on one device."""
+
+    def __init__(self, model, operand_dtype: str = "fp16", use_cuda_graph: bool = True):
+        if operand_dtype not in _DTYPES:
+            raise ValueError(f"operand_dtype must be one of {list(_DTYPES)}")
+        self.model = model
+        self.operand_dtype = operand_dtype
+        self.vtq16, self.torch16 = _DTYPES[operand_dtype]
+        self.use_cuda_graph = use_cuda_graph
+        self.device = None
+        self.ctx = None
+        self._sig = None
+        self._ws: dict[tuple[int, int], _Workspace] = {}
+        self.dump_indices = False
+
+    # ------------------------------------------------------------------ weights
+    def _signature(self):
+        return tuple((p.data_ptr(), p._version) for p in self.model.parameters())
+
+    def _ensure_ready(self):
+        p0 = next(self.model.parameters())
+        if p0.device.type != "cuda":
+            raise VtqError("vtamiq_b200: the model must live on a CUDA (sm_100) device; there is no CPU path. "
+                           "Call model.to('cuda') first.")
+        if self.device != p0.device:
+            self.device = p0.device
+            self.ctx = get_context(p0.device.index if p0.device.index is not None else torch.cuda.current_device())
+            self._sig = None
+            self._ws.clear()
+        sig = self._signature()
+        if sig != self._sig:
+            self._pack()
+            self._sig = sig
+            for ws in self._ws.values():
+                ws.graph = None  # packed buffers were re-created: captured pointers are stale
+
+    @torch.no_grad()
+    def _pack(self):
+        """(Re)build the kernel-side weight copies from the module's fp32 parameters."""
+        m, t16 = self.model, self.torch16
+        vit = m.transformer
+        emb = vit.embeddings
+        for p in m.parameters():
+            if p.dtype != torch.float32:
+                raise VtqError("vtamiq_b200 expects fp32 master parameters (model.to(device, torch.float32))")
+        f32 = lambda t: t.detach().contiguous()
+        h16 = lambda t: t.detach().to(t16).contiguous()
+        self.hidden = vit.hidden_size
+        self.heads = vit.config["num_heads"]
+        self.mlp_dim = vit.config["mlp_dim"]
+        self.num_tokens = emb.num_tokens
+        self.patch = vit.config["patch_size"]
+        self.patch_elems = 3 * self.patch * self.patch
+        if self.hidden // self.heads != 64:
+            raise VtqError("attention kernel supports head_dim 64 only")
+        if self.patch_elems % 64 != 0:
+            raise VtqError("patch size must give a K multiple of 64 for the embed GEMM")
+        if emb.use_patch_embedding:
+            self.w_pe = h16(emb.patch_embeddings.weight.reshape(self.hidden, -1))
+            self.b_pe = f32(emb.patch_embeddings.bias)
+        else:
+            self.w_pe = self.b_pe = None
+        self.cls = f32(emb.cls_token.reshape(-1)) if emb.use_cls_token else None
+        self.extra = f32(emb.extra_tokens.reshape(-1, self.hidden)) if emb.use_extra_tokens else None
+        self.n_extra = emb.num_extra_tokens
+        if emb.use_pos_embedding:
+            self.pos_table = f32(emb.positional_embeddings.positional_embeddings[0])
+            self.pos_grid = emb.positional_embeddings.width_pos_embeddings
+        else:
+            self.pos_table, self.pos_grid = None, 0
+        if emb.use_scale_embedding:
+            self.scale_table = f32(emb.scale_embeddings.scale_embeddings[0])
+            self.num_scales = emb.scale_embeddings.num_scales
+        else:
+            self.scale_table, self.num_scales = None, 0
+        self.layers = []
+        for L in vit.encoder.layers:
+            a = L.attn
+            self.layers.append(_LayerPack(
+                ln1_w=f32(L.attention_norm.weight), ln1_b=f32(L.attention_norm.bias),
+                w_qkv=h16(torch.cat([a.query.weight, a.key.weight, a.value.weight], 0)),
+                b_qkv=f32(torch.cat([a.query.bias, a.key.bias, a.value.bias], 0)),
+                w_o=h16(a.out.weight), b_o=f32(a.out.bias),
+                g1=f32(L.ls1.gamma) if vit.use_layer_scale else None,
+                ln2_w=f32(L.ffn_norm.weight), ln2_b=f32(L.ffn_norm.bias),
+                w_fc1=h16(L.ffn.fc1.weight), b_fc1=f32(L.ffn.fc1.bias),
+                w_fc2=h16(L.ffn.fc2.weight), b_fc2=f32(L.ffn.fc2.bias),
+                g2=f32(L.ls2.gamma) if vit.use_layer_scale else None,
+            ))
+        self.ln_eps = float(vit.encoder.encoder_norm.eps)
+        self.lnf_w, self.lnf_b = f32(vit.encoder.encoder_norm.weight), f32(vit.encoder.encoder_norm.bias)
+        self.diff_gamma = f32(m.diff_scale.gamma) if hasattr(m.diff_scale, "gamma") else None
+        # DiffNet + head parameter list in the order vtq_diffnet_head documents
+        plist = []
+        groups = [mod for mod in m.quality_decoder if hasattr(mod, "body")]
+        self.num_rgs = len(groups)
+        self.num_rcabs = 0
+        self.ca_hidden = 32
+        for grp in groups:
+            rcabs = list(grp.body)[:-1]
+            self.num_rcabs = len(rcabs)
+            for rc in rcabs:
+                prelu, conv, ca = rc.body[1], rc.body[2], rc.body[4]
+                if prelu.weight.numel() != 1:
+                    raise VtqError("DiffNet PReLU must have a single slope")
+                down, up = ca.conv_du[1], ca.conv_du[4]
+                self.ca_hidden = down.weight.shape[0]
+                plist += [f32(prelu.weight), f32(conv.weight.squeeze(-1)), f32(conv.bias),
+                          f32(down.weight.squeeze(-1)), f32(down.bias), f32(up.weight.squeeze(-1)), f32(up.bias)]
+            gconv = grp.body[-1]
+            plist += [f32(gconv.weight.squeeze(-1)), f32(gconv.bias)]
+        if self.num_rgs > 0:
+            fconv = m.quality_decoder[-1]
+            plist += [f32(fconv.weight.squeeze(-1)), f32(fconv.bias)]
+        else:
+            plist += [None, None]
+        lin1, pre, lin2 = m.q_predictor[1], m.q_predictor[2], m.q_predictor[4]
+        self.head_hidden = lin1.weight.shape[0]
+        plist += [f32(lin1.weight), f32(lin1.bias), f32(pre.weight), f32(lin2.weight), f32(lin2.bias)]
+        self._tail_tensors = plist  # keep alive
+        arr = (C.c_void_p * len(plist))(*[None if t is None else t.data_ptr() for t in plist])
+        self._tail_params = arr
+        self.token_num = int(getattr(m, "token_num", 0))
+
+    # ------------------------------------------------------------------ workspaces
+    def workspace(self, B: int, N: int) -> _Workspace:
+        self._ensure_ready()
+        ws = self._ws.get((B, N))
+        if ws is None:
+            ws = self._ws[(B, N)] = _Workspace(self, B, N)
+        return ws
+
+    # ------------------------------------------------------------------ launch sequence
+    def _encode_and_score(self, ws: _Workspace, embedded: bool):
+        """Everything after the inputs sit in ws.patches16 / ws.proj, ws.pos, ws.scales."""
+        c, st, dt = self.ctx.call, _stream(), self.vtq16
+        B, N, S, H = ws.B, ws.N, ws.S, self.hidden
+        n_seq, rows, prow = 2 * B, 2 * B * S, 2 * B * N
+        if not embedded:
+            c("vtq_gemm", _ptr(ws.patches16), 0, _ptr(self.w_pe), _ptr(self.b_pe), prow, H, self.patch_elems, dt,
+              EPI_BIAS_F32, _ptr(ws.proj), 0, None, st)
+        if self.dump_indices:
+            if ws.pos_idx is None:
+                ws.pos_idx = torch.zeros(prow, dtype=torch.int32, device=self.device)
+                ws.scale_idx = torch.zeros(prow, dtype=torch.int32, device=self.device)
+        c("vtq_embed_assemble", _ptr(ws.proj), _ptr(ws.pos), _ptr(ws.scales) if self.scale_table is not None else None,
+          _ptr(self.pos_table), self.pos_grid, _ptr(self.scale_table), self.num_scales, _ptr(self.cls),
+          _ptr(self.extra), self.n_extra, n_seq, N, H, _ptr(ws.x),
+          _ptr(ws.pos_idx) if self.dump_indices else None, _ptr(ws.scale_idx) if self.dump_indices else None, st)
+        eps = self.ln_eps
+        for L in self.layers:
+            c("vtq_layernorm", _ptr(ws.x), _ptr(L.ln1_w), _ptr(L.ln1_b), eps, rows, H, _ptr(ws.ln), dt, st)
+            c("vtq_gemm", _ptr(ws.ln), 0, _ptr(L.w_qkv), _ptr(L.b_qkv), rows, 3 * H, H, dt, EPI_BIAS_H,
+              _ptr(ws.qkv), 0, None, st)
+            c("vtq_attention_fwd", _ptr(ws.qkv), _ptr(ws.att), n_seq, S, self.heads, dt, st)
+            c("vtq_gemm", _ptr(ws.att), 0, _ptr(L.w_o), _ptr(L.b_o), rows, H, H, dt, EPI_BIAS_RESID_F32,
+              _ptr(ws.x), 0, _ptr(L.g1), st)
+            c("vtq_layernorm", _ptr(ws.x), _ptr(L.ln2_w), _ptr(L.ln2_b), eps, rows, H, _ptr(ws.ln), dt, st)
+            c("vtq_gemm", _ptr(ws.ln), 0, _ptr(L.w_fc1), _ptr(L.b_fc1), rows, self.mlp_dim, H, dt, EPI_BIAS_GELU_H,
+              _ptr(ws.h1), 0, None, st)
+            c("vtq_gemm", _ptr(ws.h1), 0, _ptr(L.w_fc2), _ptr(L.b_fc2), rows, H, self.mlp_dim, dt,
+              EPI_BIAS_RESID_F32, _ptr(ws.x), 0, _ptr(L.g2), st)
+        c("vtq_cls_diff", _ptr(ws.x), B, S, H, self.token_num, _ptr(self.lnf_w), _ptr(self.lnf_b), eps,
+          _ptr(self.diff_gamma), _ptr(ws.diff), st)
+        c("vtq_diffnet_head", _ptr(ws.diff), self._tail_params, len(self._tail_params), self.num_rgs, self.num_rcabs,
+          H, self.ca_hidden, self.head_hidden, B, _ptr(ws.q), _ptr(ws.tail_ws), st)
+
+    def launches_per_forward(self, embedded: bool = False) -> int:
+        """Kernels of ours in one encode+score pass (excludes the input staging kernels)."""
+        tail = 1 + self.num_rgs * (self.num_rcabs * 3 + 1) + (1 if self.num_rgs else 0) + 2
+        return (0 if embedded else 1) + 1 + 7 * len(self.layers) + tail
+
+    def run(self, ws: _Workspace, embedded: bool = False):
+        """Encode + score the staged inputs; uses a captured CUDA graph per workspace when enabled."""
+        if not self.use_cuda_graph or self.dump_indices:
+            self._encode_and_score(ws, embedded)
+            return
+        key = ("emb" if embedded else "patch")
+        if ws.graph is None or ws.graph[0] != key:
+            # warm-up outside capture (cudaFuncSetAttribute, lazy module load), then capture
+            self._encode_and_score(ws, embedded)
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._encode_and_score(ws, embedded)
+            ws.graph = (key, g)
+        ws.graph[1].replay()
+
+    # ------------------------------------------------------------------ input staging
+    def stage_patches(self, ws: _Workspace, patches, pos, scales):
+        """Reference-style inputs: tuples (ref, dist) of (B,N,3,P,P) fp32 [or (B,N,H) embedded], (B,N,2), (B,N)."""
+        c, st = self.ctx.call, _stream()
+        B, N = ws.B, ws.N
+        embedded = patches[0].dim() == 3
+        for img in range(2):
+            p = patches[img]
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                p = p.to(torch.float32).contiguous()
+            if embedded:
+                ws.proj[img * B * N:(img + 1) * B * N].copy_(p.reshape(B * N, self.hidden))
+            else:
+                c("vtq_cast_rows", _ptr(p), C.c_void_p(ws.patches16[img * B * N].data_ptr()), p.numel(), self.vtq16, st)
+            if self.pos_table is not None:
+                ws.pos[img * B * N:(img + 1) * B * N].copy_(pos[img].reshape(B * N, 2))
+            if self.scale_table is not None:
+                if scales is None or scales[img] is None:
+                    raise ValueError("Model uses scale embedding but scales is passed as None.")
+                ws.scales[img * B * N:(img + 1) * B * N].copy_(scales[img].reshape(B * N))
+        return embedded

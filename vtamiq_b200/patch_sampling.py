@@ -1,0 +1,158 @@
+"""Device-side multi-scale patch extraction — host mirror of the gather half of
+``get_iqa_patches`` (reference data/patch_sampling.py:450-613).
+
+What stays on the host, unchanged: WHERE to sample (``PatchSampler.get_sample_params`` →
+``stratified_grid_sampling``, patch_sampling.py:46-395, numpy RNG).  What moves to the GPU: the gather
+closure (:529-545), the chained 2x ``AvgPool2d`` pyramid (:552,:600), uv normalisation (:559-568) and the
+scale ids (:572-574), through ``vtq_patch_gather`` / ``vtq_avgpool2x2``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ._lib import VTQ_F16, get_context
+from .engine import _ptr, _stream
+
+DEFAULT_NUM_SAMPLES_RATIO = 1.7
+
+
+def compute_patch_num_scales(patch_num_scales, h, w, ho, wo):
+    """How many pyramid levels the image supports (patch_sampling.py:398-411)."""
+    if patch_num_scales <= 1:
+        return 1
+    side = max(ho, wo)
+    dim, possible = min(h, w), 0
+    while dim > 1:
+        possible += 1
+        dim = (dim - side) / 2
+    return max(1, min(possible - 1, patch_num_scales))
+
+
+def compute_num_patches_per_scale(patch_count, patch_num_scales, scale_num_samples_ratio):
+    """Patch budget per level, coarsest level first (patch_sampling.py:427-447): geometric weights
+    2^(ratio*i), rounded up, then trimmed from the fine end so the total is exactly ``patch_count``."""
+    counts = 2 ** (scale_num_samples_ratio * np.arange(patch_num_scales))
+    counts = np.ceil(counts * patch_count / np.sum(counts)).astype(int)
+    running = np.cumsum(counts)
+    for i in range(patch_num_scales):
+        if patch_count <= running[i]:
+            counts[i] -= running[i] - patch_count
+            counts[i + 1:] = 0
+            break
+    return counts
+
+
+def _pyramid(ctx, level0: torch.Tensor, num_levels: int):
+    """[planes..., H, W] fp32 -> list of levels; level s+1 = 2x2 mean of level s (floor mode)."""
+    levels = [level0]
+    for _ in range(1, num_levels):
+        src = levels[-1]
+        H, W = src.shape[-2:]
+        dst = torch.empty(*src.shape[:-2], H // 2, W // 2, dtype=torch.float32, device=src.device)
+        ctx.call("vtq_avgpool2x2", _ptr(src), _ptr(dst), src.numel() // (H * W), H, W, _stream())
+        levels.append(dst)
+    return levels
+
+
+def gather_into_workspace(eng, ws, images: torch.Tensor, samples):
+    """Fill ws.patches16 / ws.pos / ws.scales for ``Engine.run`` from (2,B,3,H,W) images + per-scale coords."""
+    if images.dim() != 5 or images.shape[0] != 2 or images.shape[2] != 3:
+        raise ValueError("images must be (2, B, 3, H, W)")
+    if images.dtype != torch.float32 or not images.is_contiguous():
+        images = images.to(torch.float32).contiguous()
+    B = images.shape[1]
+    levels = _pyramid(eng.ctx, images, len(samples))
+    use_scales = eng.scale_table is not None
+    off = 0
+    for s, (lvl, smp) in enumerate(zip(levels, samples)):
+        if smp.dtype != torch.float64 or smp.shape[0] != B or smp.shape[1] != 2:
+            raise ValueError("samples[s] must be float64 (B, 2, n_s)")
+        smp = smp.contiguous()
+        n = smp.shape[2]
+        H, W = lvl.shape[-2:]
+        eng.ctx.call("vtq_patch_gather", _ptr(lvl), 2 * B, H, W, _ptr(smp), B, n, off, ws.N, None,
+                     _ptr(ws.patches16), eng.vtq16, _ptr(ws.pos), _ptr(ws.scales) if use_scales else None, s,
+                     _stream())
+        off += n
+    if off != ws.N:
+        raise ValueError("sample counts do not add up to the workspace's patch count")
+
+
+def extract_patches(tensors: torch.Tensor, samples, patch_dim: int = 16, with_scales: bool | None = None):
+    """Reference-format outputs for K images sharing one coordinate set (aligned patches).
+
+    tensors : (K, 3, H, W) fp32 CUDA tensor (K=2 for FR-IQA: ref, dist)
+    samples : list over scales of float64 arrays/tensors (2, n_s)
+    returns (patches (K,N,3,P,P) fp32, pos (K,N,2) fp32, scales (K,N) int32 | None) — bit-identical to
+    ``get_iqa_patches(...)`` run with the same coordinates.
+    """
+    if patch_dim != 16:
+        raise ValueError("the gather kernel is specialised for 16x16 patches")
+    if tensors.device.type != "cuda":
+        raise RuntimeError("extract_patches runs on the GPU only (no CPU path)")
+    ctx = get_context(tensors.device.index if tensors.device.index is not None else torch.cuda.current_device())
+    if tensors.dtype != torch.float32 or not tensors.is_contiguous():
+        tensors = tensors.to(torch.float32).contiguous()
+    K = tensors.shape[0]
+    dev = tensors.device
+    smp = [torch.as_tensor(np.asarray(s), dtype=torch.float64).to(dev).reshape(1, 2, -1).contiguous() for s in samples]
+    N = int(sum(s.shape[-1] for s in smp))
+    use_scales = (len(smp) > 1) if with_scales is None else with_scales
+    patches = torch.zeros(K, N, 3, patch_dim, patch_dim, dtype=torch.float32, device=dev)
+    pos = torch.zeros(K, N, 2, dtype=torch.float32, device=dev)
+    scales = torch.zeros(K, N, dtype=torch.float32, device=dev) if use_scales else None
+    levels = _pyramid(ctx, tensors, len(smp))
+    off = 0
+    for s, (lvl, sm) in enumerate(zip(levels, smp)):
+        H, W = lvl.shape[-2:]
+        n = sm.shape[-1]
+        ctx.call("vtq_patch_gather", _ptr(lvl), K, H, W, _ptr(sm), 1, n, off, N, _ptr(patches), None, VTQ_F16,
+                 _ptr(pos), _ptr(scales), s, _stream())
+        off += n
+    return patches, pos, (scales.to(torch.int32) if use_scales else None)
+
+
+def get_iqa_patches(imgs, tensors, patch_count, patch_dim, patch_sampler, patch_num_scales,
+                    scale_num_samples_ratio=DEFAULT_NUM_SAMPLES_RATIO, use_aligned_patches=True,
+                    randomize_patch_scale_order=False, random_seed=None, debug=False):
+    """Same call signature as the reference function (patch_sampling.py:450-461).  ``patch_sampler`` is the
+    reference's own ``PatchSampler`` (or any object with ``compute_diff`` / ``get_sample_params``): it still
+    chooses the coordinates on the host with numpy's RNG; extraction happens on the GPU.
+    Only the shipped configuration is accelerated: aligned patches, scale-ordered output."""
+    if not use_aligned_patches or randomize_patch_scale_order:
+        raise NotImplementedError("vtamiq_b200.get_iqa_patches: only use_aligned_patches=True and "
+                                  "randomize_patch_scale_order=False are on the accelerated path")
+    if len(imgs) != len(tensors):
+        raise ValueError("get_iqa_patches(): Image and Tensor counts should match.")
+    if patch_count < patch_num_scales:
+        raise ValueError("get_iqa_patches(): number of patches larger than the number of scales.")
+    state = None
+    if random_seed is not None:
+        state = np.random.get_state()
+        np.random.seed(random_seed)
+    try:
+        ref = imgs[0]
+        height, width = (ref.height, ref.width) if hasattr(ref, "height") else ref.shape[:2]
+        diff = patch_sampler.compute_diff(imgs)
+        if diff is not None:
+            # difference-weighted sampling pools the weight map per level on the host; the shipped
+            # configuration (GRID_TYPE_PERTURBED_SIMPLE, patch_sampling.py:65-69) never produces one
+            raise NotImplementedError("vtamiq_b200.get_iqa_patches: difference-weighted sampling is not accelerated")
+        n_scales = compute_patch_num_scales(patch_num_scales, height, width, patch_dim, patch_dim)
+        counts = compute_num_patches_per_scale(patch_count, n_scales, scale_num_samples_ratio)
+        t = torch.stack(list(tensors), dim=0)
+        samples, h, w, total = [], t.shape[-2], t.shape[-1], 0
+        for s in range(n_scales):
+            n_s = int(counts[-s - 1])
+            samples.append(patch_sampler.get_sample_params(h, w, patch_dim, patch_dim, diff=diff, num_samples=n_s))
+            h, w = h // 2, w // 2
+            total += n_s
+            if patch_count <= total:
+                break
+    finally:
+        if state is not None:
+            np.random.set_state(state)
+    return extract_patches(t, samples, patch_dim, with_scales=n_scales > 1)

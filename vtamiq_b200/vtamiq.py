@@ -1,0 +1,154 @@
+"""Drop-in ``VTAMIQ`` module for the reference's plug point.
+
+Boundary being honoured: constructor kwargs of ``modules/vtamiq/vtamiq.py:26-46`` and
+``modules/VisionTransformer/backbone.py:17-33``; ``forward(patches, pos, scales) -> (q, None)``
+(vtamiq.py:94-119); ``set_freeze_state`` (vtamiq.py:81-92, backbone.py:62-106); identical
+``state_dict`` keys / shapes; ``transformer.load_from(npz)``.  The forward itself is the sm_100a kernel
+sequence in :mod:`vtamiq_b200.engine` — inference only, no CPU / eager fallback.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from .engine import Engine
+from .modules import (VIT_VARIANT_B16, LayerScale, VisionTransformer, _warn_unused, get_vit_config,
+                      make_quality_decoder, set_grad)
+
+
+class VisionTransformerBackbone(nn.Module):
+    """Holds ``self.transformer`` (backbone.py:8-52)."""
+
+    @property
+    def vit_hidden_size(self):
+        return self.transformer.hidden_size
+
+    @property
+    def vit_num_layers(self):
+        return len(self.transformer.encoder.layers)
+
+    def __init__(self, variant=VIT_VARIANT_B16, use_patch_embedding=True, use_pos_embedding=True,
+                 use_cls_token=True, use_classifier=True, use_layer_scale=False, pretrained=True,
+                 num_keep_layers=-1, num_adapters=0, num_scales=0, num_extra_tokens=0, path_drop_prob=0.0,
+                 return_layers=False, return_attention=False, **kwargs):
+        _warn_unused("VisionTransformerBackbone", kwargs)
+        super().__init__()
+        self.transformer = VisionTransformer(
+            config=get_vit_config(variant), use_patch_embedding=use_patch_embedding,
+            use_pos_embedding=use_pos_embedding, use_cls_token=use_cls_token, use_classifier=use_classifier,
+            use_layer_scale=use_layer_scale, num_keep_layers=num_keep_layers, num_extra_tokens=num_extra_tokens,
+            num_adapters=num_adapters, num_scales=num_scales, path_drop_prob=path_drop_prob,
+            pretrained=pretrained, return_layers=return_layers, return_attention=return_attention)
+
+    def set_freeze_state(self, freeze_state, freeze_dict):
+        """requires_grad bookkeeping only (backbone.py:62-106); kept so train.py:799,:833 keep working."""
+        rg = not freeze_state
+        every = freeze_dict is None
+        vit, emb = self.transformer, self.transformer.embeddings
+        if every or freeze_dict["freeze_encoder"]:
+            set_grad(vit.encoder, rg)
+            if not every and not freeze_dict["freeze_encoder_layerscale"] and vit.use_layer_scale:
+                for layer in vit.encoder.layers:
+                    set_grad(layer.ls1, True)
+                    set_grad(layer.ls2, True)
+        if (every or freeze_dict["freeze_embeddings_cls_token"]) and hasattr(emb, "cls_token"):
+            emb.cls_token.requires_grad = rg
+        if (every or freeze_dict["freeze_embeddings_extra_tokens"]) and hasattr(emb, "extra_tokens"):
+            emb.extra_tokens.requires_grad = rg
+        if every or freeze_dict["freeze_embeddings_patch"]:
+            set_grad(emb.patch_embeddings, rg)
+        if every or (freeze_dict["freeze_embeddings_pos"] and emb.use_pos_embedding):
+            set_grad(emb.positional_embeddings, rg)
+        if every or (freeze_dict["freeze_embeddings_scale"] and emb.use_scale_embedding):
+            set_grad(emb.scale_embeddings, rg)
+
+
+class VTAMIQ(VisionTransformerBackbone):
+    """Full-reference IQA transformer; same constructor / forward / state_dict as the reference class.
+
+    Extra, non-reference keyword arguments (all optional):
+      operand_dtype  "fp16" (default; meets the 2e-3 score-parity bar) or "bf16" — tensor-core operand type;
+                     accumulation, residual stream, LayerNorm, softmax and DiffNet are fp32 either way.
+      cuda_graph     capture the encoder + DiffNet launch sequence once per (B, N) and replay it.
+    """
+
+    def __init__(self, vit_config=None, calibrate=True, diff_scale=True, num_rgs=4, num_rcabs=4, rg_path_drop=0.1,
+                 ca_reduction=8, predictor_dropout=0., return_features=False, operand_dtype="fp16",
+                 cuda_graph=True, **kwargs):
+        vit_config = dict(vit_config) if vit_config is not None else {}
+        _warn_unused("VTAMIQ", kwargs)
+        vit_config.pop("use_classifier", None)
+        super().__init__(use_classifier=False, **vit_config, **kwargs)
+        self.token_num = 0  # which prefix token carries quality (0 -> CLS)
+        hidden = self.vit_hidden_size
+        self.diff_scale = LayerScale(hidden, init_values=1.0) if diff_scale else nn.Sequential()
+        self.quality_decoder = make_quality_decoder(hidden, num_rgs, num_rcabs, ca_reduction) if calibrate \
+            else nn.Sequential()
+        self.predictor_dropout = predictor_dropout
+        self.q_predictor = nn.Sequential(
+            nn.Dropout(predictor_dropout),
+            nn.Linear(hidden, hidden // 4),
+            nn.PReLU(),
+            nn.Dropout(predictor_dropout),
+            nn.Linear(hidden // 4, 1),
+        )
+        self.return_features = return_features
+        # not a Module / Parameter: invisible to state_dict()
+        object.__setattr__(self, "_engine", Engine(self, operand_dtype=operand_dtype, use_cuda_graph=cuda_graph))
+
+    # -- reference API ---------------------------------------------------------------------------
+    def set_freeze_state(self, freeze_state, freeze_dict):
+        print("VTAMIQ: Setting freeze state to", freeze_state)
+        super().set_freeze_state(freeze_state, freeze_dict["freeze_dict_vit"])
+        rg = not freeze_state
+        if freeze_dict["freeze_quality_decoder"]:
+            set_grad(self.quality_decoder, rg)
+        if freeze_dict["freeze_q_predictor"]:
+            set_grad(self.q_predictor, rg)
+
+    def _check_inference(self):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+            raise RuntimeError(
+                "vtamiq_b200.VTAMIQ implements the inference path only (model.eval() + torch.no_grad()); "
+                "training/backward is not provided by the sm_100a kernels")
+
+    def forward(self, patches, pos, scales):
+        """patches/pos/scales: 2-tuples (ref, dist) exactly as train.py:308 passes them → ``(q[B], None)``."""
+        self._check_inference()
+        eng = self._engine
+        p_ref = patches[0]
+        B, N = p_ref.shape[0], p_ref.shape[1]
+        if patches[1].shape != p_ref.shape:
+            raise ValueError("ref and dist patch tensors must have the same shape")
+        with torch.no_grad():
+            ws = eng.workspace(B, N)
+            embedded = eng.stage_patches(ws, patches, pos, scales)
+            eng.run(ws, embedded)
+            return ws.q.clone(), None
+
+    # -- fast entry: gather on device ------------------------------------------------------------
+    def forward_from_images(self, images, samples, return_inputs=False):
+        """Device-side patch extraction fused in front of the forward.
+
+        images  : (2, B, 3, H, W) fp32 on the model's device, already normalised ((x-.5)/.5), [0] = ref block.
+        samples : list over scales s=0.. of float64 (B, 2, n_s) top-left coordinates in the level-s image
+                  (row 0 = y), as ``PatchSampler.get_sample_params`` returns them; ref and dist share them.
+        Returns q (B,), or (q, (patches16, pos, scales)) views of the staged inputs when return_inputs.
+        """
+        from .patch_sampling import gather_into_workspace
+        self._check_inference()
+        eng = self._engine
+        with torch.no_grad():
+            B = images.shape[1]
+            N = int(sum(s.shape[-1] for s in samples))
+            ws = eng.workspace(B, N)
+            gather_into_workspace(eng, ws, images, samples)
+            eng.run(ws, embedded=False)
+            q = ws.q.clone()
+        if return_inputs:
+            return q, (ws.patches16, ws.pos, ws.scales)
+        return q
+
+    @property
+    def engine(self) -> Engine:
+        return self._engine
