@@ -1,0 +1,416 @@
+#!/usr/bin/env python
+"""Benchmark of the VTAMIQ inference hot path on B200 — BASELINE.json metric: ref/dist pairs/sec,
+ViT-B/16, 500 patches per image (configs[1]: batch 32 pairs of 512x384 images, single scale).
+
+    python bench.py --gpus 1 --steps 30 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...        # CPU arm: the reference algorithm (oracle port) on host cores
+
+One "step" = one pass of the hot path over one batch: device patch gather (images + sampled coordinates resident
+in HBM) -> patch embedding -> 12 encoder blocks for ref and dist -> CLS difference -> DiffNet -> scores, then the
+gather of the per-pair scores across ranks.  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+H_IMG, W_IMG, N_PATCH, PAIRS = 384, 512, 500, 32
+WORKLOAD = "cfg2: batch 32 pairs 512x384, 500 single-scale 16x16 patches per image, ViT-B/16 + DiffNet"
+HIDDEN, MLP, LAYERS = 768, 3072, 12
+
+
+def flops_per_pair(n_patches: int, tokens: int = 1) -> dict:
+    """Algorithmic FLOPs: 1 MAC = 2 FLOP, full dense math of the reference."""
+    S = n_patches + tokens
+    embed = 2 * n_patches * HIDDEN * HIDDEN
+    linear = LAYERS * S * 2 * (4 * HIDDEN * HIDDEN + 2 * HIDDEN * MLP)
+    attn = LAYERS * 4 * S * S * HIDDEN
+    tail = 29.79e6
+    return dict(embed=2 * embed, linear=2 * linear, attn=2 * attn, tail=tail,
+                total=2 * (embed + linear + attn) + tail)
+
+
+def peaks() -> dict:
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return dict(src="measured", hbm=d["hbm_gbs"], burst=d["bf16_tflops"], sustained=d["bf16_tflops_sustained"])
+    return dict(src="fallback", hbm=6650.0, burst=1590.0, sustained=1400.0)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons during the timed region (NVML; nvidia-smi fallback)."""
+
+    def __init__(self, index: int, period_s: float = 0.01):
+        super().__init__(daemon=True)
+        self.index, self.period, self.stop_flag = index, period_s, threading.Event()
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nvml = None
+
+    def run(self):
+        if self.nvml is None:
+            return
+        n = self.nvml
+        names = {getattr(n, k): k[len("nvmlClocksEventReason"):] for k in dir(n) if k.startswith("nvmlClocksEventReason")
+                 and isinstance(getattr(n, k), int)}
+        names.update({getattr(n, k): k[len("nvmlClocksThrottleReason"):] for k in dir(n)
+                      if k.startswith("nvmlClocksThrottleReason") and isinstance(getattr(n, k), int)
+                      and getattr(n, k) not in names})
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                try:
+                    mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if bit and (mask & bit) == bit and nm not in ("None", "All", "GpuIdle"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def result(self) -> dict:
+        self.stop_flag.set()
+        if self.nvml is None or not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        import re
+        snake = lambda nm: re.sub(r"(?<!^)(?=[A-Z])", "_", nm).lower()
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(snake(r) for r in self.reasons), "samples": len(self.sm)}
+
+
+def synth_batch(B: int, seed: int, pool: int = 4):
+    """(2,B,3,H,W) normalised fp32 images + (B,2,N) float64 coordinates; images cycle over a small pool of
+    distinct synthetic pairs (content does not change the work, generation time does)."""
+    import synth
+    rng = np.random.default_rng(seed)
+    levels = synth.graded_levels(max(pool, 2), seed)
+    base = []
+    for p in range(pool):
+        ref, dist = synth.make_pair(seed * 100 + p, H_IMG, W_IMG, float(levels[p]))
+        base.append(torch.stack([synth.to_tensor_normalized(ref), synth.to_tensor_normalized(dist)]))
+    images = torch.stack([base[b % pool] for b in range(B)], dim=1).contiguous()
+    samples = np.stack([synth.jittered_samples(rng, H_IMG, W_IMG, N_PATCH) for _ in range(B)])
+    return images, samples
+
+
+def build_model(device=None, dtype="fp16"):
+    import synth
+    import vtamiq_b200
+    torch.manual_seed(0)
+    m = vtamiq_b200.VTAMIQ(vit_config=dict(pretrained=False), operand_dtype=dtype).eval()
+    synth.perturb_(m)
+    return m.to(device) if device is not None else m
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_rate(pairs: int, repeats: int):
+    """The reference algorithm (oracle port: same ATen CPU ops as the reference, fp32) on all host cores, on a
+    bounded sample of the workload.  Returns (pairs/s best-of, cores, sample description)."""
+    from oracle import patch_oracle, vtamiq_oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    m = build_model()
+    sd = m.state_dict()
+    images, samples = synth_batch(pairs, seed=7)
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        P, POS = [], []
+        for p in range(pairs):  # the reference gathers per pair on the host (get_iqa_patches), then batches
+            pp, pos, _ = patch_oracle.extract_patches(images[:, p].numpy(), [samples[p]])
+            P.append(pp)
+            POS.append(pos)
+        P, POS = torch.from_numpy(np.stack(P)), torch.from_numpy(np.stack(POS))
+        vtamiq_oracle.vtamiq_forward(sd, (P[:, 0], P[:, 1]), (POS[:, 0], POS[:, 1]), None)
+        best = min(best, time.perf_counter() - t0)
+    return pairs / best, torch.get_num_threads(), f"{pairs} pairs x {N_PATCH} patches (gather + fp32 forward), best of {repeats}"
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pairs = 8
+    for _ in range(args.warmup):
+        pass  # the CPU arm needs no device warm-up; its first repeat warms the allocator and is not the best-of
+    t0 = time.perf_counter()
+    rate, cores, sample = cpu_reference_rate(pairs, repeats=max(2, min(args.steps, 3)))
+    line = {
+        "impl": "reference", "metric": "ref/dist pairs/sec (VTAMIQ ViT-B/16 forward, 500 patches)", "value": rate,
+        "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * pairs / rate, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "step": f"bounded sample: {pairs} pairs per step on host cores"},
+        "cpu_baseline": {"value": rate, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_gpu_arm(args):
+    import torch.distributed as dist
+    from vtamiq_b200.parallel import gather_scores
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B = PAIRS  # per GPU (weak scaling: every rank encodes its own 32 pairs)
+    model = build_model(dev, args.dtype)
+    eng = model.engine
+
+    # two distinct input sets, alternated, resident in HBM
+    sets = []
+    for s in range(2):
+        images, samples = synth_batch(B, seed=1 + 2 * rank + s)
+        sets.append((images.to(dev), [torch.from_numpy(samples).to(dev)]))
+    total_pairs = B * world
+
+    def step(i):
+        images, samples = sets[i & 1]
+        q = model.forward_from_images(images, samples)
+        return gather_scores(q, total_pairs) if world > 1 else q
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # launch accounting: one un-graphed step, counted by the library itself; then capture the CUDA graph
+    # (both before NCCL comes up, so no communicator thread is alive during stream capture)
+    eng.use_cuda_graph = False
+    model.forward_from_images(*sets[0])
+    torch.cuda.synchronize()
+    n0 = eng.ctx.launch_count()
+    model.forward_from_images(*sets[1])
+    torch.cuda.synchronize()
+    launches_per_step = eng.ctx.launch_count() - n0
+    eng.use_cuda_graph = not args.no_graph
+    model.forward_from_images(*sets[0])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        q = step(i)
+    ev1.record()
+    barrier()
+    clocks = sampler.result()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = total_pairs * args.steps / (ms / 1e3)
+
+    # ---- e2e: reference-facing call VTAMIQ.forward(patches, pos, scales) with HOST (pinned) buffers, H2D of the
+    # step's inputs and D2H of the scores inside the timed region; uploads double-buffered on a copy stream.
+    import synth  # noqa: F401
+    from vtamiq_b200 import extract_patches
+    images, samples = sets[0]
+    host_sets = []
+    with torch.no_grad():
+        for s in range(2):
+            im, sm = sets[s]
+            ws = eng.workspace(B, N_PATCH)
+            # reference-format inputs (fp32 patches, uv) produced once, outside the timed region
+            P, POS = [], []
+            for b in range(B):
+                p, pos, _ = extract_patches(im[:, b].contiguous(), [sm[0][b].cpu().numpy()])
+                P.append(p)
+                POS.append(pos)
+            P, POS = torch.stack(P, 1), torch.stack(POS, 1)     # (2,B,N,3,16,16), (2,B,N,2)
+            host_sets.append((P.cpu().pin_memory(), POS.cpu().pin_memory()))
+    dev_bufs = [(torch.empty_like(host_sets[0][0], device=dev), torch.empty_like(host_sets[0][1], device=dev))
+                for _ in range(2)]
+    q_host = torch.empty(B, dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream()
+    h2d_bytes = host_sets[0][0].numel() * 4 + host_sets[0][1].numel() * 4
+    d2h_bytes = B * 4
+
+    def upload(i):
+        hp, hpos = host_sets[i & 1]
+        dp, dpos = dev_bufs[i & 1]
+        with torch.cuda.stream(copy_stream):
+            dp.copy_(hp, non_blocking=True)
+            dpos.copy_(hpos, non_blocking=True)
+            e = torch.cuda.Event()
+            e.record(copy_stream)
+        return e
+
+    done_compute = [None, None]
+
+    def e2e_loop(n):
+        ready = upload(0)
+        for i in range(n):
+            nxt = None
+            if i + 1 < n:
+                if done_compute[(i + 1) & 1] is not None:
+                    copy_stream.wait_event(done_compute[(i + 1) & 1])   # buffer reuse: its last reader finished
+                nxt = upload(i + 1)
+            torch.cuda.current_stream().wait_event(ready)
+            dp, dpos = dev_bufs[i & 1]
+            with torch.no_grad():
+                qd, _ = model((dp[0], dp[1]), (dpos[0], dpos[1]), (None, None))
+            ev = torch.cuda.Event()
+            ev.record()
+            done_compute[i & 1] = ev
+            if world > 1:
+                qd = gather_scores(qd, total_pairs)[rank * B:(rank + 1) * B]
+            q_host.copy_(qd, non_blocking=True)
+            ready = nxt
+        torch.cuda.synchronize()
+
+    e2e_loop(max(args.warmup, 3))
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_loop(args.steps)
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    e2e_ms = max(e0.elapsed_time(e1), 0.0)
+    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = total_pairs * args.steps / (float(t.item()) / 1e3)
+
+    # ---- roofline leg (rank 0): per-launch CUDA events over instrumented (un-graphed) steps
+    roofline, breakdown = None, None
+    if rank == 0:
+        pk = peaks()
+        eng.timeline = []
+        nprof = 3
+        for i in range(nprof):
+            step(i)
+        torch.cuda.synchronize()
+        agg = {}
+        for tag, a, b in eng.timeline:
+            agg.setdefault(tag, []).append(a.elapsed_time(b))
+        eng.timeline = None
+        S = N_PATCH + 1
+        rows = 2 * B * S
+        fl = {  # algorithmic FLOPs per launch
+            "gemm_embed": 2.0 * (2 * B * N_PATCH) * HIDDEN * HIDDEN,
+            "gemm_qkv": 2.0 * rows * HIDDEN * 3 * HIDDEN,
+            "gemm_out": 2.0 * rows * HIDDEN * HIDDEN,
+            "gemm_fc1": 2.0 * rows * HIDDEN * MLP,
+            "gemm_fc2": 2.0 * rows * HIDDEN * MLP,
+            "attention": 4.0 * (2 * B) * S * S * HIDDEN,
+        }
+        breakdown = {}
+        step_ms = sum(sum(v) for v in agg.values()) / nprof
+        for tag, v in sorted(agg.items()):
+            avg = float(np.mean(v))
+            d = {"launches_per_step": len(v) // nprof, "avg_ms": round(avg, 4),
+                 "share_of_step": round(sum(v) / nprof / step_ms, 4)}
+            if tag in fl:
+                d["tflops"] = round(fl[tag] / (avg * 1e-3) / 1e12, 1)
+            breakdown[tag] = d
+        gemm_tags = [t_ for t_ in ("gemm_qkv", "gemm_out", "gemm_fc1", "gemm_fc2") if t_ in agg]
+        g_ms = sum(float(np.sum(agg[t_])) for t_ in gemm_tags) / nprof
+        g_fl = sum(fl[t_] * (len(agg[t_]) // nprof) for t_ in gemm_tags)
+        achieved = g_fl / (g_ms * 1e-3) / 1e12
+        roofline = {
+            "bound": "tensor", "kernel": "vtq::gemm_kernel (encoder QKV/out/fc1/fc2 projections, tcgen05)",
+            "achieved": round(achieved, 1), "peak": pk["sustained"], "unit": "TFLOP/s",
+            "frac": round(achieved / pk["sustained"], 4), "frac_of_burst": round(achieved / pk["burst"], 4),
+            "peak_src": f"MEASURED_PEAKS.json ({pk['src']}): bf16 sustained {pk['sustained']}, burst {pk['burst']}; "
+                        "kernel timed inside a long step -> sustained",
+            "flops_per_step": g_fl, "avg_ms_per_step": round(g_ms, 3), "share_of_step": round(g_ms / step_ms, 4),
+            "traffic": None,
+        }
+
+    # ---- CPU baseline (rank 0, N=1 only): bounded sample on the host cores
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        rate, cores, sample = cpu_reference_rate(4, repeats=2)
+        cpu = {"value": round(rate, 3), "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        fp = flops_per_pair(N_PATCH)
+        pk = peaks()
+        line = {
+            "metric": "ref/dist pairs/sec (VTAMIQ ViT-B/16 forward, 500 patches)", "value": round(value, 2),
+            "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_gpu": B, "patches": N_PATCH, "image_hw": [H_IMG, W_IMG],
+                       "operands": f"{args.dtype} tcgen05 operands, fp32 accumulate/residual/LN/softmax/DiffNet",
+                       "parallelism": f"dp{world} (pairs sharded, weight replicas, score all_gather only)",
+                       "cuda_graph": not args.no_graph,
+                       "l2": "no explicit flush: per-step working set ~0.7 GB (activations) + 151 MB images, "
+                             "two alternating input sets, >> 126 MB L2"},
+            "algorithmic_gflop_per_pair": round(fp["total"] / 1e9, 2),
+            "achieved_tflops_algorithmic": round(value / world * fp["total"] / 1e12, 1),
+            "frac_of_bf16_peak": {"burst": round(value / world * fp["total"] / 1e12 / pk["burst"], 4),
+                                  "sustained": round(value / world * fp["total"] / 1e12 / pk["sustained"], 4)},
+            "clocks": clocks,
+            "e2e": {"value": round(e2e_value, 2), "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": d2h_bytes,
+                    "api": "VTAMIQ.forward(patches, pos, scales) from pinned host fp32 patches; uploads double-buffered",
+                    "wall_s": round(wall, 3)},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "launches_per_step": int(launches_per_step),
+            "roofline": roofline, "kernels": breakdown, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -102,3 +102,18 @@ def state_hash(sd) -> str:
         h.update(k.encode())
         h.update(v.detach().cpu().contiguous().numpy().tobytes())
     return h.hexdigest()
+
+
+def select_separated(scores: np.ndarray, k: int, min_gap: float) -> np.ndarray:
+    """Indices of k pairs whose (reference) scores are pairwise >= min_gap apart, spread over the score range.
+    SRCC >= 0.9999 at batch 32 tolerates zero rank swaps, so the measurement batch must be tie-free and
+    well separated; selection uses the reference scores only."""
+    order = np.argsort(scores)
+    chosen = [order[0]]
+    for i in order[1:]:
+        if scores[i] - scores[chosen[-1]] >= min_gap:
+            chosen.append(i)
+    if len(chosen) < k:
+        raise ValueError(f"only {len(chosen)} of the requested {k} pairs are {min_gap} apart")
+    pick = np.round(np.linspace(0, len(chosen) - 1, k)).astype(int)
+    return np.sort(np.array(chosen)[pick])

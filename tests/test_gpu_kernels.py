@@ -45,7 +45,7 @@ def test_gemm_bias_h(ctx, dt, M, N, K):
     torch.cuda.synchronize()
     want = A.float() @ W.float().t() + b
     err = (out.float() - want).abs().max().item()
-    tol = 2e-2 if dt == "bf16" else 4e-3
+    tol = 4e-2 if dt == "bf16" else 4e-3   # output rounding: |out| up to ~6, eps 2^-8 / 2^-11
     assert torch.isfinite(out.float()).all()
     assert err < tol, err
 

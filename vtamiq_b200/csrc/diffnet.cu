@@ -118,8 +118,9 @@ extern "C" int vtq_diffnet_head(vtq_ctx* ctx, const float* diff, const void* con
                                 float* q, void* workspace, void* stream) {
   if (!ctx) return VTQ_ERR_INVALID;
   VTQ_CHECK_ARG(ctx, diff && params && q && workspace, "null pointer");
-  VTQ_CHECK_ARG(ctx, B >= 1 && hidden % 32 == 0 && head_hidden % 32 == 0, "shape");
-  VTQ_CHECK_ARG(ctx, num_rgs == 0 || ca_hidden % 32 == 0, "channel-attention width must be a multiple of 32");
+  VTQ_CHECK_ARG(ctx, B >= 1 && hidden % 4 == 0 && head_hidden % 4 == 0 && head_hidden >= 4, "shape");
+  VTQ_CHECK_ARG(ctx, num_rgs == 0 || (ca_hidden % 4 == 0 && ca_hidden >= 4),
+                "channel-attention width must be a multiple of 4");
   VTQ_CHECK_ARG(ctx, ca_hidden <= hidden && head_hidden <= hidden, "squeeze widths");
   VTQ_CHECK_ARG(ctx, num_rgs >= 0 && (num_rgs == 0 || num_rcabs >= 1), "each residual group needs >= 1 RCAB");
   VTQ_CHECK_ARG(ctx, DENSE_PAIRS * hidden * 4 <= ctx->smem_optin, "hidden too large for the staging tile");

@@ -89,6 +89,18 @@ class Engine:
         self._sig = None
         self._ws: dict[tuple[int, int], _Workspace] = {}
         self.dump_indices = False
+        self.timeline = None   # when a list: (tag, start_event, end_event) per launch (bench.py roofline leg)
+
+    def _call(self, tag, name, *args):
+        """ctx.call, optionally bracketed by CUDA events on the launching stream."""
+        if self.timeline is None:
+            self.ctx.call(name, *args)
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        self.ctx.call(name, *args)
+        e1.record()
+        self.timeline.append((tag, e0, e1))
 
     # ------------------------------------------------------------------ weights
     def _signature(self):
@@ -210,37 +222,38 @@ class Engine:
     # ------------------------------------------------------------------ launch sequence
     def _encode_and_score(self, ws: _Workspace, embedded: bool):
         """Everything after the inputs sit in ws.patches16 / ws.proj, ws.pos, ws.scales."""
-        c, st, dt = self.ctx.call, _stream(), self.vtq16
+        c, st, dt = self._call, _stream(), self.vtq16
         B, N, S, H = ws.B, ws.N, ws.S, self.hidden
         n_seq, rows, prow = 2 * B, 2 * B * S, 2 * B * N
         if not embedded:
-            c("vtq_gemm", _ptr(ws.patches16), 0, _ptr(self.w_pe), _ptr(self.b_pe), prow, H, self.patch_elems, dt,
-              EPI_BIAS_F32, _ptr(ws.proj), 0, None, st)
+            c("gemm_embed", "vtq_gemm", _ptr(ws.patches16), 0, _ptr(self.w_pe), _ptr(self.b_pe), prow, H,
+              self.patch_elems, dt, EPI_BIAS_F32, _ptr(ws.proj), 0, None, st)
         if self.dump_indices:
             if ws.pos_idx is None:
                 ws.pos_idx = torch.zeros(prow, dtype=torch.int32, device=self.device)
                 ws.scale_idx = torch.zeros(prow, dtype=torch.int32, device=self.device)
-        c("vtq_embed_assemble", _ptr(ws.proj), _ptr(ws.pos), _ptr(ws.scales) if self.scale_table is not None else None,
+        c("embed_assemble", "vtq_embed_assemble", _ptr(ws.proj), _ptr(ws.pos),
+          _ptr(ws.scales) if self.scale_table is not None else None,
           _ptr(self.pos_table), self.pos_grid, _ptr(self.scale_table), self.num_scales, _ptr(self.cls),
           _ptr(self.extra), self.n_extra, n_seq, N, H, _ptr(ws.x),
           _ptr(ws.pos_idx) if self.dump_indices else None, _ptr(ws.scale_idx) if self.dump_indices else None, st)
         eps = self.ln_eps
         for L in self.layers:
-            c("vtq_layernorm", _ptr(ws.x), _ptr(L.ln1_w), _ptr(L.ln1_b), eps, rows, H, _ptr(ws.ln), dt, st)
-            c("vtq_gemm", _ptr(ws.ln), 0, _ptr(L.w_qkv), _ptr(L.b_qkv), rows, 3 * H, H, dt, EPI_BIAS_H,
+            c("layernorm", "vtq_layernorm", _ptr(ws.x), _ptr(L.ln1_w), _ptr(L.ln1_b), eps, rows, H, _ptr(ws.ln), dt, st)
+            c("gemm_qkv", "vtq_gemm", _ptr(ws.ln), 0, _ptr(L.w_qkv), _ptr(L.b_qkv), rows, 3 * H, H, dt, EPI_BIAS_H,
               _ptr(ws.qkv), 0, None, st)
-            c("vtq_attention_fwd", _ptr(ws.qkv), _ptr(ws.att), n_seq, S, self.heads, dt, st)
-            c("vtq_gemm", _ptr(ws.att), 0, _ptr(L.w_o), _ptr(L.b_o), rows, H, H, dt, EPI_BIAS_RESID_F32,
+            c("attention", "vtq_attention_fwd", _ptr(ws.qkv), _ptr(ws.att), n_seq, S, self.heads, dt, st)
+            c("gemm_out", "vtq_gemm", _ptr(ws.att), 0, _ptr(L.w_o), _ptr(L.b_o), rows, H, H, dt, EPI_BIAS_RESID_F32,
               _ptr(ws.x), 0, _ptr(L.g1), st)
-            c("vtq_layernorm", _ptr(ws.x), _ptr(L.ln2_w), _ptr(L.ln2_b), eps, rows, H, _ptr(ws.ln), dt, st)
-            c("vtq_gemm", _ptr(ws.ln), 0, _ptr(L.w_fc1), _ptr(L.b_fc1), rows, self.mlp_dim, H, dt, EPI_BIAS_GELU_H,
-              _ptr(ws.h1), 0, None, st)
-            c("vtq_gemm", _ptr(ws.h1), 0, _ptr(L.w_fc2), _ptr(L.b_fc2), rows, H, self.mlp_dim, dt,
+            c("layernorm", "vtq_layernorm", _ptr(ws.x), _ptr(L.ln2_w), _ptr(L.ln2_b), eps, rows, H, _ptr(ws.ln), dt, st)
+            c("gemm_fc1", "vtq_gemm", _ptr(ws.ln), 0, _ptr(L.w_fc1), _ptr(L.b_fc1), rows, self.mlp_dim, H, dt,
+              EPI_BIAS_GELU_H, _ptr(ws.h1), 0, None, st)
+            c("gemm_fc2", "vtq_gemm", _ptr(ws.h1), 0, _ptr(L.w_fc2), _ptr(L.b_fc2), rows, H, self.mlp_dim, dt,
               EPI_BIAS_RESID_F32, _ptr(ws.x), 0, _ptr(L.g2), st)
-        c("vtq_cls_diff", _ptr(ws.x), B, S, H, self.token_num, _ptr(self.lnf_w), _ptr(self.lnf_b), eps,
+        c("cls_diff", "vtq_cls_diff", _ptr(ws.x), B, S, H, self.token_num, _ptr(self.lnf_w), _ptr(self.lnf_b), eps,
           _ptr(self.diff_gamma), _ptr(ws.diff), st)
-        c("vtq_diffnet_head", _ptr(ws.diff), self._tail_params, len(self._tail_params), self.num_rgs, self.num_rcabs,
-          H, self.ca_hidden, self.head_hidden, B, _ptr(ws.q), _ptr(ws.tail_ws), st)
+        c("diffnet_head", "vtq_diffnet_head", _ptr(ws.diff), self._tail_params, len(self._tail_params), self.num_rgs,
+          self.num_rcabs, H, self.ca_hidden, self.head_hidden, B, _ptr(ws.q), _ptr(ws.tail_ws), st)
 
     def launches_per_forward(self, embedded: bool = False) -> int:
         """Kernels of ours in one encode+score pass (excludes the input staging kernels)."""
@@ -249,7 +262,7 @@ class Engine:
 
     def run(self, ws: _Workspace, embedded: bool = False):
         """Encode + score the staged inputs; uses a captured CUDA graph per workspace when enabled."""
-        if not self.use_cuda_graph or self.dump_indices:
+        if not self.use_cuda_graph or self.dump_indices or self.timeline is not None:
             self._encode_and_score(ws, embedded)
             return
         key = ("emb" if embedded else "patch")
@@ -258,7 +271,7 @@ class Engine:
             self._encode_and_score(ws, embedded)
             torch.cuda.current_stream().synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 self._encode_and_score(ws, embedded)
             ws.graph = (key, g)
         ws.graph[1].replay()
