@@ -172,3 +172,27 @@ def test_gather_scores_gloo_world2():
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("DIST_OK") == 2, out.stdout + out.stderr
+
+
+def test_gelu_polynomial_accuracy():
+    """The fc1 epilogue's erf polynomial (csrc/gemm.cu: gelu_erf2), restated in fp32 numpy, against exact erf-GELU."""
+    import re
+    from scipy.special import erf
+    src = open(os.path.join(ROOT, "vtamiq_b200", "csrc", "gemm.cu")).read()
+    body = src[src.index("constexpr float kC[13]"):]
+    coefs = [np.float32(v) for v in re.findall(r"(-?\d\.\d+e[+-]\d+)f", body[:body.index("};")])]
+    assert len(coefs) == 13
+    x = np.linspace(-8, 8, 400001).astype(np.float32)
+    z = np.clip((x * np.float32(0.70710678118654752440)).astype(np.float32), np.float32(-3.5), np.float32(3.5))
+    u = ((z * z).astype(np.float32) * np.float32(0.16326530612244897) - np.float32(1)).astype(np.float32)
+    acc = np.full_like(x, coefs[12])
+    for c in coefs[11::-1]:
+        acc = (acc * u + c).astype(np.float32)
+    e = (z * acc).astype(np.float32)
+    h = (x * np.float32(0.5)).astype(np.float32)
+    got = (h * e + h).astype(np.float32)
+    want = 0.5 * x.astype(np.float64) * (1 + erf(x.astype(np.float64) / np.sqrt(2)))
+    assert np.abs(got - want).max() < 4e-6
+    # relative to fp16 resolution of the stored activation: well inside half an ulp wherever |gelu| >= 1e-2
+    big = np.abs(want) >= 1e-2
+    assert (np.abs(got - want)[big] / np.abs(want)[big]).max() < 2.5e-4

@@ -24,7 +24,10 @@ constexpr int ATT_THREADS = 192;
 constexpr int ATT_TILE_BYTES = 128 * ATT_D * 2;  // 16 KB: a 128-row x 64 x 16-bit tile
 constexpr int ATT_KV_STAGES = 2;
 constexpr int ATT_P_BYTES = ATT_BQ * ATT_BKV * 2;  // 32 KB
-constexpr int ATT_SMEM_BYTES = ATT_TILE_BYTES * (1 + 2 * ATT_KV_STAGES) + ATT_P_BYTES + 128 + 1024;
+// 112 KB of tiles + 128 B of barriers: two CTAs (+1 KB system reserve each) fit the SM's 228 KB.  The dynamic
+// smem base is 1024-aligned by declaration (checked at kernel entry), so no alignment slack is budgeted.
+constexpr int ATT_SMEM_BYTES = ATT_TILE_BYTES * (1 + 2 * ATT_KV_STAGES) + ATT_P_BYTES + 128;
+static_assert(2 * (ATT_SMEM_BYTES + 1024) <= 228 * 1024, "two attention CTAs must co-reside on one SM");
 constexpr uint32_t ATT_TMEM_COLS = 256;
 constexpr uint32_t ATT_TMEM_S = 0;
 constexpr uint32_t ATT_TMEM_O = 128;
@@ -33,8 +36,8 @@ template <int DT>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
     attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, int S,
                      int heads) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B-swizzle atoms need a 1024 B aligned base
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + ATT_TILE_BYTES;                   // [stages]
   uint8_t* sV = sK + ATT_KV_STAGES * ATT_TILE_BYTES;   // [stages]
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
         }
       }
       const float m_new = fmaxf(m, tmax);
-      const float alpha = exp2f((m - m_new) * c);  // m = -inf on the first tile -> 0
+      const float alpha = ex2_approx((m - m_new) * c);  // m = -inf on the first tile -> 0
       l *= alpha;
       // O correction (P V(j-1) has completed: s_full(j) was committed after it)
       if (j > 0 && __any_sync(0xffffffffu, m_new > m)) {
@@ -204,7 +207,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
         float psum = 0.f;
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
-          float v = exp2f(fmaf(__uint_as_float(r[e]), c, -mc));
+          float v = ex2_approx(fmaf(__uint_as_float(r[e]), c, -mc));
           if (cc * 32 + e >= kv_valid) v = 0.f;
           p[e] = v;
           psum += v;

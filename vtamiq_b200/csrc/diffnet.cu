@@ -5,8 +5,8 @@
 //   RCAB : y = W1 prelu_a(x) + b1 ;  h = relu(Wd y + bd) ;  x' = x + y * sigmoid(Wu h + bu)
 //   RG   : g' = g + (Wg RCAB^n(g) + bg)
 //   tail : z = Wf RG^m(d) + bf ;  q = wq . prelu(Wh z + bh) + bq
-// One launch per dense layer (the chain is strictly sequential); vtq_diffnet_head issues the whole chain from
-// C in one call so the host sees a single operator, and the chain is CUDA-graph capturable.
+// The chain is strictly sequential (each layer needs the complete previous activation), so the whole decoder runs
+// as ONE persistent cooperative kernel with a device-scope barrier between layers (diffnet_fused_kernel).
 // Reference: modules/RCAN/channel_attention.py:13-86, modules/vtamiq/vtamiq.py:12-23,:71-77,:114-117.
 #include "common.cuh"
 #include "host.h"
@@ -16,90 +16,154 @@ namespace vtq {
 enum : int { PRE_NONE = 0, PRE_PRELU = 1 };
 enum : int { DEPI_NONE = 0, DEPI_RELU = 1, DEPI_ADD = 2, DEPI_GATE = 3, DEPI_PRELU = 4 };
 
-constexpr int DENSE_PAIRS = 32;   // pairs per block (one per lane in the epilogue)
-constexpr int DENSE_WARPS = 8;    // output channels per block (one per warp)
+constexpr int DENSE_PAIRS = 32;    // pairs per tile (one per lane in the epilogue)
+constexpr int DENSE_THREADS = 256;  // 8 warps
+constexpr int MAX_LAYERS = 64;
 
-// out[b][o] = epi( sum_i W[o][i] * pre(in[b][i]) + bias[o] )
-// block: stage pre(in[b0:b0+32][:]) in smem; warp w owns channel o = blockIdx.x*8 + w; lanes split the
-// reduction (stride-32, conflict-free LDS, coalesced weight reads), 32 running sums (one per pair) per lane.
-template <int PRE, int EPI>
-__global__ void __launch_bounds__(DENSE_WARPS * 32) dense_kernel(
-    const float* __restrict__ in, int in_dim, const float* __restrict__ W, const float* __restrict__ bias,
-    int out_dim, int B, const float* __restrict__ pre_param, float* __restrict__ out,
-    const float* __restrict__ res, const float* __restrict__ gate, const float* __restrict__ epi_param) {
-  extern __shared__ float xs[];  // [DENSE_PAIRS][in_dim]
-  const int b0 = blockIdx.y * DENSE_PAIRS;
-  const int nb = min(DENSE_PAIRS, B - b0);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+struct DenseLayer {
+  const float* W;          // [out_dim][in_dim]
+  const float* bias;       // [out_dim]
+  const float* in;         // [B][in_dim]
+  float* out;              // [B][out_dim]
+  const float* res;        // [B][out_dim] or null
+  const float* gate;       // [B][out_dim] or null
+  const float* pre_param;  // PReLU slope applied to the input, or null
+  const float* epi_param;  // PReLU slope applied to the output, or null
+  int in_dim, out_dim, pre, epi;
+};
+struct LayerList {
+  DenseLayer l[MAX_LAYERS];
+  int n;
+};
 
-  float a_pre = 0.f;
-  if constexpr (PRE == PRE_PRELU) a_pre = __ldg(pre_param);
-  const int nvec = in_dim >> 2;
-  for (int idx = threadIdx.x; idx < DENSE_PAIRS * nvec; idx += blockDim.x) {
-    const int p = idx / nvec, v = idx % nvec;
-    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p < nb) {
-      t = __ldg(reinterpret_cast<const float4*>(in + static_cast<size_t>(b0 + p) * in_dim) + v);
-      if constexpr (PRE == PRE_PRELU) {
-        t.x = t.x > 0.f ? t.x : a_pre * t.x;
-        t.y = t.y > 0.f ? t.y : a_pre * t.y;
-        t.z = t.z > 0.f ? t.z : a_pre * t.z;
-        t.w = t.w > 0.f ? t.w : a_pre * t.w;
-      }
-    }
-    reinterpret_cast<float4*>(xs)[idx] = t;
-  }
-  __syncthreads();
-
-  const int o = blockIdx.x * DENSE_WARPS + warp;
-  if (o >= out_dim) return;
-  float acc[DENSE_PAIRS];
-#pragma unroll
-  for (int p = 0; p < DENSE_PAIRS; ++p) acc[p] = 0.f;
-  const float* wrow = W + static_cast<size_t>(o) * in_dim;
-  for (int k = lane; k < in_dim; k += 32) {
-    const float w = __ldg(wrow + k);
-#pragma unroll
-    for (int p = 0; p < DENSE_PAIRS; ++p) acc[p] = fmaf(w, xs[p * in_dim + k], acc[p]);
-  }
-  float mine = 0.f;
-#pragma unroll
-  for (int p = 0; p < DENSE_PAIRS; ++p) {
-    float v = acc[p];
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-    if (lane == p) mine = v;
-  }
-  if (lane < nb) {
-    const size_t oi = static_cast<size_t>(b0 + lane) * out_dim + o;
-    float v = mine + __ldg(bias + o);
-    if constexpr (EPI == DEPI_RELU) v = fmaxf(v, 0.f);
-    if constexpr (EPI == DEPI_ADD) v = res[oi] + v;
-    if constexpr (EPI == DEPI_GATE) v = res[oi] + gate[oi] * (1.0f / (1.0f + expf(-v)));
-    if constexpr (EPI == DEPI_PRELU) {
-      const float a = __ldg(epi_param);
-      v = v > 0.f ? v : a * v;
-    }
-    out[oi] = v;
-  }
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
 
-template <int PRE, int EPI>
-static int dense(vtq_ctx* ctx, const float* in, int in_dim, const float* W, const float* bias, int out_dim, int B,
-                 const float* pre_param, float* out, const float* res, const float* gate, const float* epi_param,
-                 cudaStream_t st) {
-  auto kern = dense_kernel<PRE, EPI>;
-  const int smem = DENSE_PAIRS * in_dim * static_cast<int>(sizeof(float));
-  static int configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return check_cuda(ctx, e, "diffnet: cudaFuncSetAttribute");
-    configured = smem;
+// Whole decoder + head in ONE persistent launch.  grid = (G, T): the G CTAs of a column split every layer's output
+// channels and meet at a device-scope barrier between layers (each layer needs the complete previous activation);
+// the T columns work on different 32-pair tiles.  Per layer and CTA: stage pre(in[tile]) in smem (L1-bypassing
+// loads: other CTAs wrote it), warp w takes channel pairs, lanes split the reduction (conflict-free LDS, coalesced
+// weight rows), a 31-shuffle transposing reduction leaves pair p's sum on lane p, fused bias / gate / skip epilogue.
+// The next layer's weight slice is prefetched into L2 before waiting at the barrier (weights do not depend on the
+// activations), so DRAM latency overlaps the barrier.
+__global__ void __launch_bounds__(DENSE_THREADS, 1)
+    diffnet_fused_kernel(const __grid_constant__ LayerList L, int B, unsigned* __restrict__ counters) {
+  extern __shared__ float xs[];  // [DENSE_PAIRS][in_dim]
+  const int G = gridDim.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (B + DENSE_PAIRS - 1) / DENSE_PAIRS;
+  unsigned* counter = counters + blockIdx.y * 32;  // one 128 B line per column
+  unsigned target = 0;
+
+  for (int tile = blockIdx.y; tile < n_tiles; tile += gridDim.y) {
+    const int b0 = tile * DENSE_PAIRS;
+    const int nb = min(DENSE_PAIRS, B - b0);
+    for (int li = 0; li < L.n; ++li) {
+      const DenseLayer& ly = L.l[li];
+      const int in_dim = ly.in_dim, out_dim = ly.out_dim;
+      const int chunk = (out_dim + G - 1) / G;
+      const int c0 = blockIdx.x * chunk;
+      const int nch = max(0, min(chunk, out_dim - c0));
+
+      // L2 prefetch of this CTA's weight slice (independent of the barrier)
+      {
+        const char* wbase = reinterpret_cast<const char*>(ly.W + static_cast<size_t>(c0) * in_dim);
+        const int bytes = nch * in_dim * 4;
+        for (int off = threadIdx.x * 128; off < bytes; off += DENSE_THREADS * 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(wbase + off));
+      }
+      // wait until every CTA of this column has published the previous layer
+      if (threadIdx.x == 0 && target > 0) {
+        unsigned spins = 0;
+        while (ld_acquire(counter) < target) {
+          if (++spins > (1u << 26)) __trap();
+        }
+      }
+      __syncthreads();
+
+      if (nch > 0) {
+        float a_pre = 0.f;
+        if (ly.pre == PRE_PRELU) a_pre = __ldg(ly.pre_param);
+        const int nvec = in_dim >> 2;
+        for (int idx = threadIdx.x; idx < DENSE_PAIRS * nvec; idx += DENSE_THREADS) {
+          const int p = idx / nvec, v = idx - p * nvec;
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p < nb) {
+            t = __ldcg(reinterpret_cast<const float4*>(ly.in + static_cast<size_t>(b0 + p) * in_dim) + v);
+            if (ly.pre == PRE_PRELU) {
+              t.x = t.x > 0.f ? t.x : a_pre * t.x;
+              t.y = t.y > 0.f ? t.y : a_pre * t.y;
+              t.z = t.z > 0.f ? t.z : a_pre * t.z;
+              t.w = t.w > 0.f ? t.w : a_pre * t.w;
+            }
+          }
+          reinterpret_cast<float4*>(xs)[idx] = t;
+        }
+        __syncthreads();
+
+        for (int cp = warp; cp * 2 < nch; cp += DENSE_THREADS / 32) {
+          const int ch_a = c0 + cp * 2;
+          const bool has_b = (cp * 2 + 1) < nch;
+          const float* wa = ly.W + static_cast<size_t>(ch_a) * in_dim;
+          const float* wb = has_b ? wa + in_dim : wa;
+          float acc_a[DENSE_PAIRS], acc_b[DENSE_PAIRS];
+#pragma unroll
+          for (int p = 0; p < DENSE_PAIRS; ++p) acc_a[p] = acc_b[p] = 0.f;
+#pragma unroll 2
+          for (int k = lane; k < in_dim; k += 32) {
+            const float va = __ldg(wa + k), vb = __ldg(wb + k);
+#pragma unroll
+            for (int p = 0; p < DENSE_PAIRS; ++p) {
+              const float xv = xs[p * in_dim + k];
+              acc_a[p] = fmaf(va, xv, acc_a[p]);
+              acc_b[p] = fmaf(vb, xv, acc_b[p]);
+            }
+          }
+          // transposing butterfly: after the 5 steps lane p holds sum over lanes of acc[p]
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < off; ++i) {
+              const float sa = upper ? acc_a[i] : acc_a[i + off];
+              const float ka = upper ? acc_a[i + off] : acc_a[i];
+              acc_a[i] = ka + __shfl_xor_sync(0xffffffffu, sa, off);
+              const float sb = upper ? acc_b[i] : acc_b[i + off];
+              const float kb = upper ? acc_b[i + off] : acc_b[i];
+              acc_b[i] = kb + __shfl_xor_sync(0xffffffffu, sb, off);
+            }
+          }
+          if (lane < nb) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              if (h == 1 && !has_b) break;
+              const int ch = ch_a + h;
+              const size_t oi = static_cast<size_t>(b0 + lane) * out_dim + ch;
+              float v = (h ? acc_b[0] : acc_a[0]) + __ldg(ly.bias + ch);
+              if (ly.epi == DEPI_RELU) v = fmaxf(v, 0.f);
+              else if (ly.epi == DEPI_ADD) v = __ldcg(ly.res + oi) + v;
+              else if (ly.epi == DEPI_GATE) v = __ldcg(ly.res + oi) + __ldcg(ly.gate + oi) * (1.0f / (1.0f + expf(-v)));
+              else if (ly.epi == DEPI_PRELU) {
+                const float a = __ldg(ly.epi_param);
+                v = v > 0.f ? v : a * v;
+              }
+              ly.out[oi] = v;
+            }
+          }
+        }
+      }
+      // publish this layer: every thread's stores, then one release increment per CTA
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+      }
+      target += G;
+    }
   }
-  dim3 grid((out_dim + DENSE_WARPS - 1) / DENSE_WARPS, (B + DENSE_PAIRS - 1) / DENSE_PAIRS);
-  kern<<<grid, DENSE_WARPS * 32, smem, st>>>(in, in_dim, W, bias, out_dim, B, pre_param, out, res, gate, epi_param);
-  VTQ_CHECK_LAUNCH(ctx, "diffnet dense launch");
-  return VTQ_OK;
 }
 
 }  // namespace vtq
@@ -109,8 +173,8 @@ using namespace vtq;
 extern "C" int64_t vtq_workspace_bytes(const vtq_ctx* ctx, int B, int hidden) {
   (void)ctx;
   if (B < 0 || hidden < 0) return 0;
-  // x, y, g (hidden wide) + one hidden-wide scratch for the squeeze / head activations
-  return static_cast<int64_t>(4) * B * hidden * static_cast<int64_t>(sizeof(float));
+  // 32 KB of barrier counters, then x, y, g (hidden wide) + one hidden-wide scratch for squeeze / head activations
+  return 32768 + static_cast<int64_t>(4) * B * hidden * static_cast<int64_t>(sizeof(float));
 }
 
 extern "C" int vtq_diffnet_head(vtq_ctx* ctx, const float* diff, const void* const* params, int n_params,
@@ -123,23 +187,36 @@ extern "C" int vtq_diffnet_head(vtq_ctx* ctx, const float* diff, const void* con
                 "channel-attention width must be a multiple of 4");
   VTQ_CHECK_ARG(ctx, ca_hidden <= hidden && head_hidden <= hidden, "squeeze widths");
   VTQ_CHECK_ARG(ctx, num_rgs >= 0 && (num_rgs == 0 || num_rcabs >= 1), "each residual group needs >= 1 RCAB");
-  VTQ_CHECK_ARG(ctx, DENSE_PAIRS * hidden * 4 <= ctx->smem_optin, "hidden too large for the staging tile");
+  const int smem = DENSE_PAIRS * hidden * static_cast<int>(sizeof(float));
+  VTQ_CHECK_ARG(ctx, smem <= ctx->smem_optin, "hidden too large for the staging tile");
   const int expect = num_rgs * (num_rcabs * 7 + 2) + 2 + 5;
   VTQ_CHECK_ARG(ctx, n_params == expect, "parameter list length");
+  const int n_layers = num_rgs * (num_rcabs * 3 + 1) + (num_rgs > 0 ? 1 : 0) + 2;
+  VTQ_CHECK_ARG(ctx, n_layers <= MAX_LAYERS, "too many DiffNet layers for one launch");
   for (int i = 0; i < n_params; ++i) {
     const bool final_conv = (i == num_rgs * (num_rcabs * 7 + 2) || i == num_rgs * (num_rcabs * 7 + 2) + 1);
     VTQ_CHECK_ARG(ctx, params[i] != nullptr || (final_conv && num_rgs == 0), "null parameter");
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t plane = static_cast<size_t>(B) * hidden;
-  float* xbuf = static_cast<float*>(workspace);
+  unsigned* counters = static_cast<unsigned*>(workspace);        // first 32 KB: barrier counters
+  float* xbuf = reinterpret_cast<float*>(static_cast<char*>(workspace) + 32768);
   float* ybuf = xbuf + plane;
   float* gbuf = ybuf + plane;
   float* hbuf = gbuf + plane;
   auto P = [&](int i) { return static_cast<const float*>(params[i]); };
 
+  LayerList L;
+  L.n = 0;
+  auto add = [&](const float* in, int in_dim, const float* W, const float* bias, int out_dim, int pre,
+                 const float* pre_param, int epi, float* out, const float* res, const float* gate,
+                 const float* epi_param) {
+    DenseLayer& d = L.l[L.n++];
+    d.W = W; d.bias = bias; d.in = in; d.out = out; d.res = res; d.gate = gate;
+    d.pre_param = pre_param; d.epi_param = epi_param;
+    d.in_dim = in_dim; d.out_dim = out_dim; d.pre = pre; d.epi = epi;
+  };
   int pi = 0;
-  int rc;
   const float* g_in = diff;  // group input (skip source)
   for (int g = 0; g < num_rgs; ++g) {
     const float* x_in = g_in;
@@ -147,41 +224,51 @@ extern "C" int vtq_diffnet_head(vtq_ctx* ctx, const float* diff, const void* con
       const float *a = P(pi), *W1 = P(pi + 1), *b1 = P(pi + 2), *Wd = P(pi + 3), *bd = P(pi + 4), *Wu = P(pi + 5),
                   *bu = P(pi + 6);
       pi += 7;
-      if ((rc = dense<PRE_PRELU, DEPI_NONE>(ctx, x_in, hidden, W1, b1, hidden, B, a, ybuf, nullptr, nullptr,
-                                            nullptr, st)))
-        return rc;
-      if ((rc = dense<PRE_NONE, DEPI_RELU>(ctx, ybuf, hidden, Wd, bd, ca_hidden, B, nullptr, hbuf, nullptr, nullptr,
-                                           nullptr, st)))
-        return rc;
-      if ((rc = dense<PRE_NONE, DEPI_GATE>(ctx, hbuf, ca_hidden, Wu, bu, hidden, B, nullptr, xbuf, x_in, ybuf,
-                                           nullptr, st)))
-        return rc;
+      add(x_in, hidden, W1, b1, hidden, PRE_PRELU, a, DEPI_NONE, ybuf, nullptr, nullptr, nullptr);
+      add(ybuf, hidden, Wd, bd, ca_hidden, PRE_NONE, nullptr, DEPI_RELU, hbuf, nullptr, nullptr, nullptr);
+      add(hbuf, ca_hidden, Wu, bu, hidden, PRE_NONE, nullptr, DEPI_GATE, xbuf, x_in, ybuf, nullptr);
       x_in = xbuf;
     }
-    const float *Wg = P(pi), *bg = P(pi + 1);
+    add(x_in, hidden, P(pi), P(pi + 1), hidden, PRE_NONE, nullptr, DEPI_ADD, gbuf, g_in, nullptr, nullptr);
     pi += 2;
-    if ((rc = dense<PRE_NONE, DEPI_ADD>(ctx, x_in, hidden, Wg, bg, hidden, B, nullptr, gbuf, g_in, nullptr, nullptr,
-                                        st)))
-      return rc;
     g_in = gbuf;
   }
   const float* z = g_in;
-  {
-    const float *Wf = P(pi), *bf = P(pi + 1);
-    pi += 2;
-    if (num_rgs > 0) {
-      if ((rc = dense<PRE_NONE, DEPI_NONE>(ctx, g_in, hidden, Wf, bf, hidden, B, nullptr, ybuf, nullptr, nullptr,
-                                           nullptr, st)))
-        return rc;
-      z = ybuf;
-    }
+  if (num_rgs > 0) {
+    add(g_in, hidden, P(pi), P(pi + 1), hidden, PRE_NONE, nullptr, DEPI_NONE, ybuf, nullptr, nullptr, nullptr);
+    z = ybuf;
   }
-  const float *Wh = P(pi), *bh = P(pi + 1), *ah = P(pi + 2), *Wq = P(pi + 3), *bq = P(pi + 4);
-  if ((rc = dense<PRE_NONE, DEPI_PRELU>(ctx, z, hidden, Wh, bh, head_hidden, B, nullptr, hbuf, nullptr, nullptr, ah,
-                                        st)))
-    return rc;
-  if ((rc = dense<PRE_NONE, DEPI_NONE>(ctx, hbuf, head_hidden, Wq, bq, 1, B, nullptr, q, nullptr, nullptr, nullptr,
-                                       st)))
-    return rc;
+  pi += 2;
+  add(z, hidden, P(pi), P(pi + 1), head_hidden, PRE_NONE, nullptr, DEPI_PRELU, hbuf, nullptr, nullptr, P(pi + 2));
+  add(hbuf, head_hidden, P(pi + 3), P(pi + 4), 1, PRE_NONE, nullptr, DEPI_NONE, q, nullptr, nullptr, nullptr);
+
+  // grid: T columns of G CTAs, all co-resident (cooperative launch): G*T <= #SMs
+  const int n_tiles = (B + DENSE_PAIRS - 1) / DENSE_PAIRS;
+  int T = n_tiles < 8 ? n_tiles : 8;
+  int G = ctx->num_sms / T;
+  if (G > 96) G = 96;
+  if (G < 1) G = 1;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(diffnet_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         ctx->smem_optin < 200 * 1024 ? ctx->smem_optin : 200 * 1024);
+    if (e != cudaSuccess) return check_cuda(ctx, e, "diffnet: cudaFuncSetAttribute");
+    configured = true;
+  }
+  cudaError_t e = cudaMemsetAsync(counters, 0, 32768, st);
+  if (e != cudaSuccess) return check_cuda(ctx, e, "diffnet: cudaMemsetAsync");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(G, T, 1);
+  cfg.blockDim = dim3(DENSE_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, diffnet_fused_kernel, L, B, counters);
+  if (e != cudaSuccess) return check_cuda(ctx, e, "diffnet: cooperative launch");
+  VTQ_CHECK_LAUNCH(ctx, "diffnet fused launch");
   return VTQ_OK;
 }

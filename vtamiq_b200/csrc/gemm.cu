@@ -31,7 +31,28 @@ struct GemmCfg {
 
 enum : int { EPI_H = 0, EPI_F32 = 1 };
 
-__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+// erf-GELU on two values at once, fp32 throughout (packed FFMA2).  erf(z) = z * P(u), u = z^2 * (2/3.5^2) - 1,
+// P = degree-12 Chebyshev fit of erf(z)/z on |z| <= 3.5 re-expanded in u (well conditioned on [-1,1]);
+// |z| is clamped to 3.5 where erf is within 7.4e-7 of +-1.  Max |erf error| 6.5e-7, max |gelu error| 1.7e-6
+// (tests/test_host_logic.py::test_gelu_polynomial_accuracy restates and checks the same coefficients).
+// The epilogue is issue-bound next to a K=768 mainloop: this is ~11 issue slots per element instead of ~25 for
+// erff().
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+  constexpr float kC[13] = {4.038730562e-01f, -2.007001489e-01f, 1.467439830e-01f, -1.146334782e-01f,
+                            8.848482370e-02f, -6.463798881e-02f, 4.461858794e-02f, -3.037289716e-02f,
+                            1.790029742e-02f, -6.848857272e-03f, 3.642286174e-03f, -4.138993565e-03f,
+                            1.783549204e-03f};
+  const float z0 = fminf(fmaxf(x0 * 0.70710678118654752440f, -3.5f), 3.5f);
+  const float z1 = fminf(fmaxf(x1 * 0.70710678118654752440f, -3.5f), 3.5f);
+  const f32x2 z = f2_pack(z0, z1);
+  const f32x2 u = f2_fma(f2_mul(z, z), f2_pack(0.16326530612244897f, 0.16326530612244897f), f2_pack(-1.0f, -1.0f));
+  f32x2 acc = f2_pack(kC[12], kC[12]);
+#pragma unroll
+  for (int i = 11; i >= 0; --i) acc = f2_fma(acc, u, f2_pack(kC[i], kC[i]));
+  const f32x2 e = f2_mul(z, acc);                       // erf(x / sqrt2)
+  const f32x2 h = f2_mul(f2_pack(x0, x1), f2_pack(0.5f, 0.5f));
+  f2_unpack(f2_fma(h, e, h), x0, x1);                   // 0.5 x (1 + erf)
+}
 
 template <int DT, int BN, int EPI, bool GELU>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -221,7 +242,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
               v[7] = __uint_as_float(r[8 * j + 7]) + b1.w;
               if constexpr (GELU) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = gelu_erf(v[e]);
+                for (int e = 0; e < 8; e += 2) gelu_erf2(v[e], v[e + 1]);
               }
               const uint32_t chunk = static_cast<uint32_t>(hh * 4 + j);
               st_shared_v4(row_addr + ((chunk ^ swz) << 4), pack2<DT>(v[0], v[1]), pack2<DT>(v[2], v[3]),

@@ -257,8 +257,7 @@ class Engine:
 
     def launches_per_forward(self, embedded: bool = False) -> int:
         """Kernels of ours in one encode+score pass (excludes the input staging kernels)."""
-        tail = 1 + self.num_rgs * (self.num_rcabs * 3 + 1) + (1 if self.num_rgs else 0) + 2
-        return (0 if embedded else 1) + 1 + 7 * len(self.layers) + tail
+        return (0 if embedded else 1) + 1 + 7 * len(self.layers) + 2   # + cls_diff + fused DiffNet/head
 
     def run(self, ws: _Workspace, embedded: bool = False):
         """Encode + score the staged inputs; uses a captured CUDA graph per workspace when enabled."""
