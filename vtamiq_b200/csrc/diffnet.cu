@@ -45,13 +45,32 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
 // Whole decoder + head in ONE persistent launch.  grid = (G, T): the G CTAs of a column split every layer's output
 // channels and meet at a device-scope barrier between layers (each layer needs the complete previous activation);
 // the T columns work on different 32-pair tiles.  Per layer and CTA: stage pre(in[tile]) in smem (L1-bypassing
-// loads: other CTAs wrote it), warp w takes channel pairs, lanes split the reduction (conflict-free LDS, coalesced
-// weight rows), a 31-shuffle transposing reduction leaves pair p's sum on lane p, fused bias / gate / skip epilogue.
-// The next layer's weight slice is prefetched into L2 before waiting at the barrier (weights do not depend on the
-// activations), so DRAM latency overlaps the barrier.
+// cp.async: other CTAs wrote it); warp w takes a pair of channels; lane i owns input columns {128 j + 4 i .. +3}
+// (conflict-free 128-bit LDS of weights and activations), accumulating even/odd columns in packed fp32x2 FMAs;
+// a 31-shuffle transposing reduction leaves pair p's sum on lane p; fused bias / gate / skip epilogue.
+// The CTA's weight rows are copied to smem with cp.async issued BEFORE it waits at the barrier (weights do not
+// depend on activations), so the DRAM latency of the weight stream overlaps the barrier.
+constexpr int DENSE_KV = 8;       // float4 per lane per weight row: in_dim <= 1024
+constexpr int DENSE_WROWS = 16;   // weight rows staged in smem per round (8 warps x 2 channels)
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// stage rows [c, c+n) of W (n <= DENSE_WROWS) into ws[n][in_dim] with 16-byte async copies
+__device__ __forceinline__ void stage_weights(float* ws, const float* __restrict__ W, int c, int n, int in_dim) {
+  const int nvec = in_dim >> 2;
+  const float4* src = reinterpret_cast<const float4*>(W + static_cast<size_t>(c) * in_dim);
+  for (int idx = threadIdx.x; idx < n * nvec; idx += DENSE_THREADS) cp_async16(reinterpret_cast<float4*>(ws) + idx, src + idx);
+}
+
 __global__ void __launch_bounds__(DENSE_THREADS, 1)
-    diffnet_fused_kernel(const __grid_constant__ LayerList L, int B, unsigned* __restrict__ counters) {
-  extern __shared__ float xs[];  // [DENSE_PAIRS][in_dim]
+    diffnet_fused_kernel(const __grid_constant__ LayerList L, int B, int max_dim, unsigned* __restrict__ counters) {
+  extern __shared__ __align__(16) float smem_f[];
+  float* xs = smem_f;                              // [DENSE_PAIRS][in_dim]   activations of this tile
+  float* ws = smem_f + DENSE_PAIRS * max_dim;      // [DENSE_WROWS][in_dim]   weight rows of this round
   const int G = gridDim.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (B + DENSE_PAIRS - 1) / DENSE_PAIRS;
@@ -64,17 +83,14 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1)
     for (int li = 0; li < L.n; ++li) {
       const DenseLayer& ly = L.l[li];
       const int in_dim = ly.in_dim, out_dim = ly.out_dim;
+      const int nvec = in_dim >> 2;
       const int chunk = (out_dim + G - 1) / G;
       const int c0 = blockIdx.x * chunk;
       const int nch = max(0, min(chunk, out_dim - c0));
 
-      // L2 prefetch of this CTA's weight slice (independent of the barrier)
-      {
-        const char* wbase = reinterpret_cast<const char*>(ly.W + static_cast<size_t>(c0) * in_dim);
-        const int bytes = nch * in_dim * 4;
-        for (int off = threadIdx.x * 128; off < bytes; off += DENSE_THREADS * 128)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(wbase + off));
-      }
+      // round 0 of this CTA's weight rows: in flight while we wait at the barrier (weights do not depend on it)
+      if (nch > 0) stage_weights(ws, ly.W, c0, min(nch, DENSE_WROWS), in_dim);
+      cp_async_commit();
       // wait until every CTA of this column has published the previous layer
       if (threadIdx.x == 0 && target > 0) {
         unsigned spins = 0;
@@ -85,75 +101,105 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1)
       __syncthreads();
 
       if (nch > 0) {
-        float a_pre = 0.f;
-        if (ly.pre == PRE_PRELU) a_pre = __ldg(ly.pre_param);
-        const int nvec = in_dim >> 2;
-        for (int idx = threadIdx.x; idx < DENSE_PAIRS * nvec; idx += DENSE_THREADS) {
-          const int p = idx / nvec, v = idx - p * nvec;
-          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p < nb) {
-            t = __ldcg(reinterpret_cast<const float4*>(ly.in + static_cast<size_t>(b0 + p) * in_dim) + v);
-            if (ly.pre == PRE_PRELU) {
-              t.x = t.x > 0.f ? t.x : a_pre * t.x;
-              t.y = t.y > 0.f ? t.y : a_pre * t.y;
-              t.z = t.z > 0.f ? t.z : a_pre * t.z;
-              t.w = t.w > 0.f ? t.w : a_pre * t.w;
-            }
+        // activations: async 16-byte copies straight to smem (L2 -> smem, L1 bypassed: other CTAs wrote them)
+        for (int idx = threadIdx.x; idx < nb * nvec; idx += DENSE_THREADS)
+          cp_async16(reinterpret_cast<float4*>(xs) + idx,
+                     reinterpret_cast<const float4*>(ly.in + static_cast<size_t>(b0) * in_dim) + idx);
+        cp_async_commit();
+        cp_async_wait_all();
+        if (ly.pre == PRE_PRELU) {  // each thread fixes up exactly the elements it copied
+          const float a_pre = __ldg(ly.pre_param);
+          for (int idx = threadIdx.x; idx < nb * nvec; idx += DENSE_THREADS) {
+            float4 t = reinterpret_cast<float4*>(xs)[idx];
+            t.x = t.x > 0.f ? t.x : a_pre * t.x;
+            t.y = t.y > 0.f ? t.y : a_pre * t.y;
+            t.z = t.z > 0.f ? t.z : a_pre * t.z;
+            t.w = t.w > 0.f ? t.w : a_pre * t.w;
+            reinterpret_cast<float4*>(xs)[idx] = t;
           }
-          reinterpret_cast<float4*>(xs)[idx] = t;
         }
+        for (int idx = nb * nvec + threadIdx.x; idx < DENSE_PAIRS * nvec; idx += DENSE_THREADS)
+          reinterpret_cast<float4*>(xs)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);  // ragged last tile
         __syncthreads();
 
-        for (int cp = warp; cp * 2 < nch; cp += DENSE_THREADS / 32) {
-          const int ch_a = c0 + cp * 2;
-          const bool has_b = (cp * 2 + 1) < nch;
-          const float* wa = ly.W + static_cast<size_t>(ch_a) * in_dim;
-          const float* wb = has_b ? wa + in_dim : wa;
-          float acc_a[DENSE_PAIRS], acc_b[DENSE_PAIRS];
+        for (int r0 = 0; r0 < nch; r0 += DENSE_WROWS) {
+          const int nr = min(DENSE_WROWS, nch - r0);
+          if (r0 > 0) {  // later rounds (a CTA owns more than 16 channels only when many tiles share the SMs)
+            __syncthreads();
+            stage_weights(ws, ly.W, c0 + r0, nr, in_dim);
+            cp_async_commit();
+            cp_async_wait_all();
+            __syncthreads();
+          }
+          if (warp * 2 < nr) {
+            const int ch_a = c0 + r0 + warp * 2;
+            const bool has_b = (warp * 2 + 1) < nr;
+            const float* wra = ws + (warp * 2) * in_dim;
+            const float* wrb = has_b ? wra + in_dim : wra;
+            f32x2 acc_a[DENSE_PAIRS], acc_b[DENSE_PAIRS];  // (even-column sum, odd-column sum)
 #pragma unroll
-          for (int p = 0; p < DENSE_PAIRS; ++p) acc_a[p] = acc_b[p] = 0.f;
-#pragma unroll 2
-          for (int k = lane; k < in_dim; k += 32) {
-            const float va = __ldg(wa + k), vb = __ldg(wb + k);
+            for (int p = 0; p < DENSE_PAIRS; ++p) acc_a[p] = acc_b[p] = 0ull;
+#pragma unroll 1
+            for (int k = lane * 4; k < in_dim; k += 128) {
+              const float4 wa = *reinterpret_cast<const float4*>(wra + k);
+              const float4 wb = *reinterpret_cast<const float4*>(wrb + k);
+              const f32x2 a01 = f2_pack(wa.x, wa.y), a23 = f2_pack(wa.z, wa.w);
+              const f32x2 b01 = f2_pack(wb.x, wb.y), b23 = f2_pack(wb.z, wb.w);
+#pragma unroll
+              for (int p = 0; p < DENSE_PAIRS; ++p) {
+                const float4 xv = *reinterpret_cast<const float4*>(xs + p * in_dim + k);
+                const f32x2 x01 = f2_pack(xv.x, xv.y), x23 = f2_pack(xv.z, xv.w);
+                acc_a[p] = f2_fma(a01, x01, acc_a[p]);
+                acc_a[p] = f2_fma(a23, x23, acc_a[p]);
+                acc_b[p] = f2_fma(b01, x01, acc_b[p]);
+                acc_b[p] = f2_fma(b23, x23, acc_b[p]);
+              }
+            }
+            float ra[DENSE_PAIRS], rb[DENSE_PAIRS];
 #pragma unroll
             for (int p = 0; p < DENSE_PAIRS; ++p) {
-              const float xv = xs[p * in_dim + k];
-              acc_a[p] = fmaf(va, xv, acc_a[p]);
-              acc_b[p] = fmaf(vb, xv, acc_b[p]);
+              float lo, hi;
+              f2_unpack(acc_a[p], lo, hi);
+              ra[p] = lo + hi;
+              f2_unpack(acc_b[p], lo, hi);
+              rb[p] = lo + hi;
             }
-          }
-          // transposing butterfly: after the 5 steps lane p holds sum over lanes of acc[p]
+            // transposing butterfly: after the 5 steps lane p holds the sum over lanes of r[p]
 #pragma unroll
-          for (int off = 16; off >= 1; off >>= 1) {
-            const bool upper = (lane & off) != 0;
+            for (int off = 16; off >= 1; off >>= 1) {
+              const bool upper = (lane & off) != 0;
 #pragma unroll
-            for (int i = 0; i < off; ++i) {
-              const float sa = upper ? acc_a[i] : acc_a[i + off];
-              const float ka = upper ? acc_a[i + off] : acc_a[i];
-              acc_a[i] = ka + __shfl_xor_sync(0xffffffffu, sa, off);
-              const float sb = upper ? acc_b[i] : acc_b[i + off];
-              const float kb = upper ? acc_b[i + off] : acc_b[i];
-              acc_b[i] = kb + __shfl_xor_sync(0xffffffffu, sb, off);
-            }
-          }
-          if (lane < nb) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              if (h == 1 && !has_b) break;
-              const int ch = ch_a + h;
-              const size_t oi = static_cast<size_t>(b0 + lane) * out_dim + ch;
-              float v = (h ? acc_b[0] : acc_a[0]) + __ldg(ly.bias + ch);
-              if (ly.epi == DEPI_RELU) v = fmaxf(v, 0.f);
-              else if (ly.epi == DEPI_ADD) v = __ldcg(ly.res + oi) + v;
-              else if (ly.epi == DEPI_GATE) v = __ldcg(ly.res + oi) + __ldcg(ly.gate + oi) * (1.0f / (1.0f + expf(-v)));
-              else if (ly.epi == DEPI_PRELU) {
-                const float a = __ldg(ly.epi_param);
-                v = v > 0.f ? v : a * v;
+              for (int i = 0; i < off; ++i) {
+                const float sa = upper ? ra[i] : ra[i + off];
+                const float ka = upper ? ra[i + off] : ra[i];
+                ra[i] = ka + __shfl_xor_sync(0xffffffffu, sa, off);
+                const float sb = upper ? rb[i] : rb[i + off];
+                const float kb = upper ? rb[i + off] : rb[i];
+                rb[i] = kb + __shfl_xor_sync(0xffffffffu, sb, off);
               }
-              ly.out[oi] = v;
+            }
+            if (lane < nb) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                if (h == 1 && !has_b) break;
+                const int ch = ch_a + h;
+                const size_t oi = static_cast<size_t>(b0 + lane) * out_dim + ch;
+                float v = (h ? rb[0] : ra[0]) + __ldg(ly.bias + ch);
+                if (ly.epi == DEPI_RELU) v = fmaxf(v, 0.f);
+                else if (ly.epi == DEPI_ADD) v = __ldcg(ly.res + oi) + v;
+                else if (ly.epi == DEPI_GATE)
+                  v = __ldcg(ly.res + oi) + __ldcg(ly.gate + oi) * (1.0f / (1.0f + expf(-v)));
+                else if (ly.epi == DEPI_PRELU) {
+                  const float a = __ldg(ly.epi_param);
+                  v = v > 0.f ? v : a * v;
+                }
+                ly.out[oi] = v;
+              }
             }
           }
         }
+      } else {
+        cp_async_wait_all();
       }
       // publish this layer: every thread's stores, then one release increment per CTA
       __syncthreads();
@@ -182,12 +228,13 @@ extern "C" int vtq_diffnet_head(vtq_ctx* ctx, const float* diff, const void* con
                                 float* q, void* workspace, void* stream) {
   if (!ctx) return VTQ_ERR_INVALID;
   VTQ_CHECK_ARG(ctx, diff && params && q && workspace, "null pointer");
-  VTQ_CHECK_ARG(ctx, B >= 1 && hidden % 4 == 0 && head_hidden % 4 == 0 && head_hidden >= 4, "shape");
+  VTQ_CHECK_ARG(ctx, B >= 1 && hidden % 4 == 0 && hidden <= 128 * DENSE_KV && head_hidden % 4 == 0 && head_hidden >= 4,
+                "shape (hidden must be a multiple of 4, <= 1024)");
   VTQ_CHECK_ARG(ctx, num_rgs == 0 || (ca_hidden % 4 == 0 && ca_hidden >= 4),
                 "channel-attention width must be a multiple of 4");
   VTQ_CHECK_ARG(ctx, ca_hidden <= hidden && head_hidden <= hidden, "squeeze widths");
   VTQ_CHECK_ARG(ctx, num_rgs >= 0 && (num_rgs == 0 || num_rcabs >= 1), "each residual group needs >= 1 RCAB");
-  const int smem = DENSE_PAIRS * hidden * static_cast<int>(sizeof(float));
+  const int smem = (DENSE_PAIRS + DENSE_WROWS) * hidden * static_cast<int>(sizeof(float));
   VTQ_CHECK_ARG(ctx, smem <= ctx->smem_optin, "hidden too large for the staging tile");
   const int expect = num_rgs * (num_rcabs * 7 + 2) + 2 + 5;
   VTQ_CHECK_ARG(ctx, n_params == expect, "parameter list length");
@@ -267,7 +314,7 @@ extern "C" int vtq_diffnet_head(vtq_ctx* ctx, const float* diff, const void* con
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, diffnet_fused_kernel, L, B, counters);
+  e = cudaLaunchKernelEx(&cfg, diffnet_fused_kernel, L, B, hidden, counters);
   if (e != cudaSuccess) return check_cuda(ctx, e, "diffnet: cooperative launch");
   VTQ_CHECK_LAUNCH(ctx, "diffnet fused launch");
   return VTQ_OK;
