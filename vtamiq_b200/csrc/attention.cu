@@ -148,32 +148,42 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
     const uint32_t p_row = smem_u32(sP) + row * 128;
     const float c = 0.125f * 1.44269504088896340736f;  // (1/sqrt(64)) * log2(e)
 
-    float m = -INFINITY;  // running max of the raw (unscaled) scores
+    float m = -INFINITY;  // reference max of the raw (unscaled) scores that P and O are currently scaled by
     float l = 0.f;        // running sum of exp
+    const f32x2 c2 = f2_pack(c, c);
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int kv_valid = S - j * ATT_BKV;  // keys of this tile that exist (>= 1)
 
-      // pass 1: row maximum
-      float tmax = -INFINITY;
+      // pass 1: row maximum (3-input max; only the chunk straddling the sequence end pays for masking)
+      float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll 1
       for (int cc = 0; cc < ATT_BKV / 32; ++cc) {
-        if (cc * 32 >= kv_valid) break;
+        const int rem = kv_valid - cc * 32;
+        if (rem <= 0) break;
         uint32_t r[32];
         tmem_ld32(t_lane + ATT_TMEM_S + cc * 32, r);
         tmem_wait_ld();
+        if (rem < 32) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const float s = __uint_as_float(r[e]);
-          if (cc * 32 + e < kv_valid) tmax = fmaxf(tmax, s);
+          for (int e = 0; e < 32; ++e)
+            if (e >= rem) r[e] = 0xff800000u;  // -inf
+        }
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          mx0 = fmax3(mx0, __uint_as_float(r[e]), __uint_as_float(r[e + 1]));
+          mx1 = fmax3(mx1, __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
         }
       }
-      const float m_new = fmaxf(m, tmax);
-      const float alpha = ex2_approx((m - m_new) * c);  // m = -inf on the first tile -> 0
-      l *= alpha;
-      // O correction (P V(j-1) has completed: s_full(j) was committed after it)
-      if (j > 0 && __any_sync(0xffffffffu, m_new > m)) {
+      float m_new = fmaxf(m, fmaxf(mx0, mx1));
+      // Lazy rescale: keep the old reference max while the true max grew by < 2^8 in the exp2 domain — P then
+      // stays <= 256 (exact in fp16/bf16 range, fp32 sums) and O needs no correction.  First tile: m = -inf.
+      if ((m_new - m) * c <= 8.0f) m_new = m;
+      if (j > 0 && __any_sync(0xffffffffu, m_new != m)) {
+        // O correction (P V(j-1) has completed: s_full(j) was committed after it)
+        const float alpha = ex2_approx((m - m_new) * c);
+        l *= alpha;
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           uint32_t r[32];
@@ -186,13 +196,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
         tmem_wait_st();
       }
       m = m_new;
-      const float mc = m_new * c;
+      const float nmc = -m_new * c;
+      const f32x2 nmc2 = f2_pack(nmc, nmc);
 
-      // pass 2: p = exp2(s*c - m*c), row sum, 16-bit P into swizzled smem
+      // pass 2: p = exp2(s*c - m*c) (packed FFMA2 + MUFU.EX2), packed row sums, 16-bit P into swizzled smem
+      f32x2 sum2 = 0ull;
 #pragma unroll 1
       for (int cc = 0; cc < ATT_BKV / 32; ++cc) {
         const uint32_t blk = p_row + (cc >> 1) * 16384;
-        if (cc * 32 >= kv_valid) {
+        const int rem = kv_valid - cc * 32;
+        if (rem <= 0) {
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
             const uint32_t chunk = static_cast<uint32_t>((cc & 1) * 4 + jj);
@@ -203,23 +216,29 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
         uint32_t r[32];
         tmem_ld32(t_lane + ATT_TMEM_S + cc * 32, r);
         tmem_wait_ld();
-        float p[32];
-        float psum = 0.f;
+        uint32_t pk[16];
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          float v = ex2_approx(fmaf(__uint_as_float(r[e]), c, -mc));
-          if (cc * 32 + e >= kv_valid) v = 0.f;
-          p[e] = v;
-          psum += v;
+        for (int e = 0; e < 32; e += 2) {
+          float t0, t1;
+          f2_unpack(f2_fma(f2_pack(__uint_as_float(r[e]), __uint_as_float(r[e + 1])), c2, nmc2), t0, t1);
+          float p0 = ex2_approx(t0), p1 = ex2_approx(t1);
+          if (rem < 32) {  // warp-uniform; only the straddling chunk
+            if (e >= rem) p0 = 0.f;
+            if (e + 1 >= rem) p1 = 0.f;
+          }
+          sum2 = f2_add(sum2, f2_pack(p0, p1));
+          pk[e >> 1] = pack2<DT>(p0, p1);
         }
-        l += psum;
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           const uint32_t chunk = static_cast<uint32_t>((cc & 1) * 4 + jj);
-          st_shared_v4(blk + ((chunk ^ swz) << 4), pack2<DT>(p[8 * jj + 0], p[8 * jj + 1]),
-                       pack2<DT>(p[8 * jj + 2], p[8 * jj + 3]), pack2<DT>(p[8 * jj + 4], p[8 * jj + 5]),
-                       pack2<DT>(p[8 * jj + 6], p[8 * jj + 7]));
+          st_shared_v4(blk + ((chunk ^ swz) << 4), pk[4 * jj + 0], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
         }
+      }
+      {
+        float s0, s1;
+        f2_unpack(sum2, s0, s1);
+        l += s0 + s1;
       }
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();

@@ -1,33 +1,36 @@
 // K3/K5 — dense projection  out = epilogue(A[M][K] · W[N][K]^T + bias)  on the 5th-gen tensor cores.
 //
-// Persistent, warp-specialised, one CTA per SM:
-//   warp 0      TMA producer   : A tile 128x64 and W tile BNx64 (16-bit, 128B swizzle) into a smem ring
-//   warp 1      MMA issuer     : tcgen05.mma.cta_group::1.kind::f16, M=128 N=BN K=16, fp32 accumulators in
-//                                TMEM, two accumulator buffers so the epilogue of tile i overlaps tile i+1
-//   warps 2..5  epilogue       : tcgen05.ld (one TMEM lane = one output row per thread), bias / erf-GELU /
-//                                LayerScale in registers, 128B-swizzled staging in smem, then per-warp TMA
-//                                store — or TMA reduce-add for the fp32 residual stream, so the residual
+// Two persistent, warp-specialised kernels share one epilogue:
+//
+//  gemm2_kernel  (default, M >= 256)  CTA PAIR = 2-CTA cluster on one TPC, tcgen05.mma.cta_group::2, tile 256 x BN.
+//      Each CTA TMA-loads its own 128 rows of A and HALF of the W tile (BN/2 rows); the leader CTA's single MMA
+//      thread issues M=256 N=BN K=16 instructions that read both CTAs' smem and write each CTA's 128 x BN fp32
+//      accumulator into its own TMEM.  Per output tile this halves the W bytes pulled from L2 and the W bytes read
+//      from smem per SM — the 1-CTA kernel measured L2-/smem-bound (profiles/), not tensor-bound.
+//  gemm_kernel   (small M, or VTQ_GEMM_1CTA=1)  single CTA, cta_group::1, tile 128 x BN.
+//
+// Roles (both kernels, 320 threads):
+//   warp 0      TMA producer   : 16-bit tiles, 128B swizzle, into a multi-stage smem ring (mbarrier expect_tx)
+//   warp 1      MMA issuer     : one elected thread; accumulators double-buffered in TMEM so the epilogue of
+//                                tile i overlaps the mainloop of tile i+1
+//   warps 2..9  epilogue       : tcgen05.ld (one TMEM lane = one output row per thread), bias / erf-GELU /
+//                                LayerScale in registers, 128B-swizzled staging in smem, per-warp TMA store —
+//                                or TMA reduce-add for the fp32 residual stream, so the residual
 //                                read-modify-write never travels through the SM.
 // Replaces the ATen addmm/conv calls listed in include/vtamiq_b200.h (vtq_gemm).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "host.h"
 
 namespace vtq {
 
-constexpr int GEMM_BM = 128;
-constexpr int GEMM_BK = 64;  // 64 x 16-bit = one 128-byte swizzle row
-constexpr int GEMM_THREADS = 192;
-constexpr int GEMM_STAGING_BYTES = 4 * 2 * 4096;  // 4 epilogue warps x 2 buffers x (32 rows x 128 B)
-
-template <int BN>
-struct GemmCfg {
-  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-  static constexpr int B_BYTES = BN * GEMM_BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
-  static constexpr int TMEM_COLS = 2 * BN;  // double-buffered accumulator
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_STAGING_BYTES + 256 /*barriers*/ + 1024 /*align*/;
-};
+constexpr int GEMM_BM = 128;  // rows per CTA
+constexpr int GEMM_BK = 64;   // 64 x 16-bit = one 128-byte swizzle row
+constexpr int GEMM_EPI_WARPS = 8;   // two per SM sub-partition: the GELU epilogue is issue-bound with one
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
+constexpr int GEMM_STAGING_BYTES = GEMM_EPI_WARPS * 4096;  // one 32-row x 128 B staging box per epilogue warp
+constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;
 
 enum : int { EPI_H = 0, EPI_F32 = 1 };
 
@@ -54,15 +57,117 @@ __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
   f2_unpack(f2_fma(h, e, h), x0, x1);                   // 0.5 x (1 + erf)
 }
 
+// ------------------------------------------------------------------------------------------------
+// Epilogue of one 128 x BN accumulator for one warp: 32 rows (its TMEM lane quarter) x every second column chunk
+// (`half` = 0/1: the two warps sharing a lane quarter interleave chunks).  The caller signals "accumulator free"
+// after this returns (all TMEM reads of the warp are complete by then).
+// ------------------------------------------------------------------------------------------------
+template <int DT, int BN, int EPI, bool GELU>
+__device__ __forceinline__ void epilogue_tile(uint32_t t_row, int row0, int n0, int N, const float* __restrict__ bias,
+                                              const float* __restrict__ gamma, int accumulate,
+                                              const CUtensorMap* tmO, uint8_t* buf, int lane, int half) {
+  const uint32_t swz = static_cast<uint32_t>(lane & 7);
+  if constexpr (EPI == EPI_F32) {
+    // 32 fp32 columns (128 B per row) per staged box
+#pragma unroll 1
+    for (int c = half; c < BN / 32; c += 2) {
+      const int ncol = n0 + c * 32;
+      if (ncol >= N) break;
+      uint32_t r[32];
+      tmem_ld32(t_row + c * 32, r);
+      tmem_wait_ld();
+      if (lane == 0) tma_wait_group_read<0>();  // the previous store has finished reading the staging box
+      __syncwarp();
+      const uint32_t row_addr = smem_u32(buf) + lane * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 bv = __ldg(reinterpret_cast<const float4*>(bias + ncol) + j);
+        float v0 = __uint_as_float(r[4 * j + 0]) + bv.x;
+        float v1 = __uint_as_float(r[4 * j + 1]) + bv.y;
+        float v2 = __uint_as_float(r[4 * j + 2]) + bv.z;
+        float v3 = __uint_as_float(r[4 * j + 3]) + bv.w;
+        if (gamma != nullptr) {
+          float4 gv = __ldg(reinterpret_cast<const float4*>(gamma + ncol) + j);
+          v0 *= gv.x; v1 *= gv.y; v2 *= gv.z; v3 *= gv.w;
+        }
+        st_shared_v4(row_addr + ((static_cast<uint32_t>(j) ^ swz) << 4), __float_as_uint(v0), __float_as_uint(v1),
+                     __float_as_uint(v2), __float_as_uint(v3));
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (accumulate) tma_reduce_add_2d(tmO, buf, ncol, row0);
+        else tma_store_2d(tmO, buf, ncol, row0);
+        tma_commit_group();
+      }
+    }
+  } else {
+    // 64 16-bit columns (128 B per row) per staged box = two TMEM loads
+#pragma unroll 1
+    for (int c = half; c < BN / 64; c += 2) {
+      const int ncol = n0 + c * 64;
+      if (ncol >= N) break;
+      if (lane == 0) tma_wait_group_read<0>();
+      __syncwarp();
+      const uint32_t row_addr = smem_u32(buf) + lane * 128;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t r[32];
+        tmem_ld32(t_row + c * 64 + hh * 32, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + ncol + hh * 32) + 2 * j);
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + ncol + hh * 32) + 2 * j + 1);
+          float v[8];
+          v[0] = __uint_as_float(r[8 * j + 0]) + b0.x;
+          v[1] = __uint_as_float(r[8 * j + 1]) + b0.y;
+          v[2] = __uint_as_float(r[8 * j + 2]) + b0.z;
+          v[3] = __uint_as_float(r[8 * j + 3]) + b0.w;
+          v[4] = __uint_as_float(r[8 * j + 4]) + b1.x;
+          v[5] = __uint_as_float(r[8 * j + 5]) + b1.y;
+          v[6] = __uint_as_float(r[8 * j + 6]) + b1.z;
+          v[7] = __uint_as_float(r[8 * j + 7]) + b1.w;
+          if constexpr (GELU) {
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) gelu_erf2(v[e], v[e + 1]);
+          }
+          const uint32_t chunk = static_cast<uint32_t>(hh * 4 + j);
+          st_shared_v4(row_addr + ((chunk ^ swz) << 4), pack2<DT>(v[0], v[1]), pack2<DT>(v[2], v[3]),
+                       pack2<DT>(v[4], v[5]), pack2<DT>(v[6], v[7]));
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tmO, buf, ncol, row0);
+        tma_commit_group();
+      }
+    }
+  }
+}
+
+// ================================================================================================
+// 1-CTA kernel
+// ================================================================================================
+template <int BN>
+struct GemmCfg {
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = GEMM_A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int ACC_STRIDE = (BN > 128) ? 256 : 128;  // TMEM columns between the two accumulators
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_STAGING_BYTES + 256 /*barriers*/;
+};
+
 template <int DT, int BN, int EPI, bool GELU>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmO, const float* __restrict__ bias,
                 const float* __restrict__ gamma, int M, int N, int K, int accumulate) {
   using Cfg = GemmCfg<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  // 128B swizzle atoms are 1024 B: align the ring and the staging buffers.
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B-swizzle atoms need a 1024 B aligned base
   uint8_t* ring = smem;
   uint8_t* staging = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + GEMM_STAGING_BYTES);
@@ -90,7 +195,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 128);
+      mbar_init(&acc_empty[a], GEMM_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -110,7 +215,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = ring + stage * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + Cfg::A_BYTES;
+          uint8_t* sb = sa + GEMM_A_BYTES;
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m0);
           tma_load_2d(sb, &tmB, &full_bar[stage], kb * GEMM_BK, n0);
@@ -130,12 +235,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(ring + stage * Cfg::STAGE_BYTES);
-          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint32_t sb = sa + GEMM_A_BYTES;
           const uint64_t da = umma_smem_desc(sa, 16, 1024);
           const uint64_t db = umma_smem_desc(sb, 16, 1024);
 #pragma unroll
@@ -152,112 +257,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     __syncwarp();
   } else {
     // ------------------------------- epilogue -----------------------------------
-    const int ew = warp - 2;             // staging slot
-    const int lane_grp = warp & 3;       // TMEM lanes this warp may touch: [32*lane_grp, +32)
-    uint8_t* my_staging = staging + ew * 8192;
-    const uint32_t swz = static_cast<uint32_t>(lane & 7);
-    uint32_t n_store = 0;
+    const int lane_grp = warp & 3;  // TMEM lanes this warp may touch: [32*lane_grp, +32)
+    const int half = (warp - 2) >> 2;
+    uint8_t* my_staging = staging + (warp - 2) * 4096;
     uint32_t it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int m0 = (t / num_n) * GEMM_BM;
       const int n0 = (t % num_n) * BN;
       const uint32_t acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&acc_full[acc], acc_phase);
+      mbar_wait(&acc_full[acc], (it >> 1) & 1);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + acc * BN;
-      const int row0 = m0 + lane_grp * 32;  // first output row of this warp's 32-row slab
-
-      if constexpr (EPI == EPI_F32) {
-        // 32 fp32 columns (128 B per row) per staged box
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          const int ncol = n0 + c * 32;
-          if (ncol >= N) break;
-          uint32_t r[32];
-          tmem_ld32(t_row + c * 32, r);
-          tmem_wait_ld();
-          if (c == BN / 32 - 1 || ncol + 32 >= N) {  // last read of this accumulator
-            tc_fence_before();
-            mbar_arrive(&acc_empty[acc]);
-          }
-          uint8_t* buf = my_staging + (n_store & 1) * 4096;
-          if (lane == 0) tma_wait_group_read<1>();
-          __syncwarp();
-          const uint32_t row_addr = smem_u32(buf) + lane * 128;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 bv = __ldg(reinterpret_cast<const float4*>(bias + ncol) + j);
-            float v0 = __uint_as_float(r[4 * j + 0]) + bv.x;
-            float v1 = __uint_as_float(r[4 * j + 1]) + bv.y;
-            float v2 = __uint_as_float(r[4 * j + 2]) + bv.z;
-            float v3 = __uint_as_float(r[4 * j + 3]) + bv.w;
-            if (gamma != nullptr) {
-              float4 gv = __ldg(reinterpret_cast<const float4*>(gamma + ncol) + j);
-              v0 *= gv.x; v1 *= gv.y; v2 *= gv.z; v3 *= gv.w;
-            }
-            st_shared_v4(row_addr + ((static_cast<uint32_t>(j) ^ swz) << 4), __float_as_uint(v0),
-                         __float_as_uint(v1), __float_as_uint(v2), __float_as_uint(v3));
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            if (accumulate) tma_reduce_add_2d(&tmO, buf, ncol, row0);
-            else tma_store_2d(&tmO, buf, ncol, row0);
-            tma_commit_group();
-          }
-          ++n_store;
-        }
-      } else {
-        // 64 16-bit columns (128 B per row) per staged box = two TMEM loads
-#pragma unroll 1
-        for (int c = 0; c < BN / 64; ++c) {
-          const int ncol = n0 + c * 64;
-          if (ncol >= N) break;
-          uint8_t* buf = my_staging + (n_store & 1) * 4096;
-          if (lane == 0) tma_wait_group_read<1>();
-          __syncwarp();
-          const uint32_t row_addr = smem_u32(buf) + lane * 128;
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            uint32_t r[32];
-            tmem_ld32(t_row + c * 64 + hh * 32, r);
-            tmem_wait_ld();
-            if (hh == 1 && (c == BN / 64 - 1 || ncol + 64 >= N)) {
-              tc_fence_before();
-              mbar_arrive(&acc_empty[acc]);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + ncol + hh * 32) + 2 * j);
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + ncol + hh * 32) + 2 * j + 1);
-              float v[8];
-              v[0] = __uint_as_float(r[8 * j + 0]) + b0.x;
-              v[1] = __uint_as_float(r[8 * j + 1]) + b0.y;
-              v[2] = __uint_as_float(r[8 * j + 2]) + b0.z;
-              v[3] = __uint_as_float(r[8 * j + 3]) + b0.w;
-              v[4] = __uint_as_float(r[8 * j + 4]) + b1.x;
-              v[5] = __uint_as_float(r[8 * j + 5]) + b1.y;
-              v[6] = __uint_as_float(r[8 * j + 6]) + b1.z;
-              v[7] = __uint_as_float(r[8 * j + 7]) + b1.w;
-              if constexpr (GELU) {
-#pragma unroll
-                for (int e = 0; e < 8; e += 2) gelu_erf2(v[e], v[e + 1]);
-              }
-              const uint32_t chunk = static_cast<uint32_t>(hh * 4 + j);
-              st_shared_v4(row_addr + ((chunk ^ swz) << 4), pack2<DT>(v[0], v[1]), pack2<DT>(v[2], v[3]),
-                           pack2<DT>(v[4], v[5]), pack2<DT>(v[6], v[7]));
-            }
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmO, buf, ncol, row0);
-            tma_commit_group();
-          }
-          ++n_store;
-        }
-      }
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + acc * Cfg::ACC_STRIDE;
+      epilogue_tile<DT, BN, EPI, GELU>(t_row, m0 + lane_grp * 32, n0, N, bias, gamma, accumulate, &tmO, my_staging,
+                                       lane, half);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);  // one arrival per epilogue warp
     }
     if (lane == 0) tma_wait_group<0>();  // all bulk stores retired before the CTA's smem goes away
   }
@@ -267,13 +282,210 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
+// ================================================================================================
+// 2-CTA (CTA pair) kernel
+// ================================================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are credited to the LEADER CTA's mbarrier (peer bit cleared)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this smem offset in BOTH CTAs of the pair once all prior MMAs have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+// arrive on the same-offset mbarrier of cluster CTA `rank`
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+template <uint32_t COLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_holder) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_holder)),
+               "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t COLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;  // this CTA's half of the W tile
+  static constexpr int STAGE_BYTES = GEMM_A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 128) ? 8 : 6;
+  static constexpr int ACC_STRIDE = (BN > 128) ? 256 : 128;
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_STAGING_BYTES + 256;
+  static_assert(STAGE_BYTES % 1024 == 0, "stage bases must stay 1024 B aligned");
+  static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
+};
+
+template <int DT, int BN, int EPI, bool GELU>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+    gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmO, const float* __restrict__ bias,
+                 const float* __restrict__ gamma, int M, int N, int K, int accumulate) {
+  using Cfg = Gemm2Cfg<BN>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* ring = smem;
+  uint8_t* staging = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + GEMM_STAGING_BYTES);
+  uint64_t* full_bar = bars;                          // [STAGES]  used in the leader; both CTAs' TMA credit it
+  uint64_t* empty_bar = bars + Cfg::STAGES;           // [STAGES]  per CTA; arrived by the leader's multicast commit
+  uint64_t* acc_full = bars + 2 * Cfg::STAGES;        // [2]       per CTA; multicast commit
+  uint64_t* acc_empty = bars + 2 * Cfg::STAGES + 2;   // [2]       leader only: 8 epilogue warps (both CTAs) arrive
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  const int num_m = (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  const int num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = K / GEMM_BK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 2 * GEMM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_holder);
+  tc_fence_before();
+  cluster_sync_all();  // barrier inits + TMEM allocation visible in both CTAs before any remote arrival
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer (both CTAs) -------------------
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        const int m0 = (t / num_n) * (2 * GEMM_BM) + static_cast<int>(rank) * GEMM_BM;
+        const int n0 = (t % num_n) * BN + static_cast<int>(rank) * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = ring + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + GEMM_A_BYTES;
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);  // both CTAs' bytes land here
+          tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m0);
+          tma_load_2d_pair(sb, &tmB, &full_bar[stage], kb * GEMM_BK, n0);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer (leader CTA only) ---------------
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(DT, 2 * GEMM_BM, BN, 0, 0);
+      uint32_t stage = 0, phase = 0;
+      uint32_t it = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
+        const uint32_t acc = it & 1;
+        mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(ring + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + GEMM_A_BYTES;
+          const uint64_t da = umma_smem_desc(sa, 16, 1024);
+          const uint64_t db = umma_smem_desc(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            umma_f16_ss_pair(d_tmem, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit_pair(&empty_bar[stage]);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(&acc_full[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------- epilogue (both CTAs, own 128 rows) ----------
+    const int lane_grp = warp & 3;
+    const int half = (warp - 2) >> 2;
+    uint8_t* my_staging = staging + (warp - 2) * 4096;
+    uint32_t it = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
+      const int m0 = (t / num_n) * (2 * GEMM_BM) + static_cast<int>(rank) * GEMM_BM;
+      const int n0 = (t % num_n) * BN;
+      const uint32_t acc = it & 1;
+      mbar_wait(&acc_full[acc], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + acc * Cfg::ACC_STRIDE;
+      epilogue_tile<DT, BN, EPI, GELU>(t_row, m0 + lane_grp * 32, n0, N, bias, gamma, accumulate, &tmO, my_staging,
+                                       lane, half);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(&acc_empty[acc], 0);  // one arrival per epilogue warp, on the leader
+    }
+    if (lane == 0) tma_wait_group<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // no CTA may exit (or free TMEM) while its pair still signals its barriers / reads its smem
+  if (warp == 1) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
+}
+
 // ------------------------------------------------------------------------------------------------
 // host launcher
 // ------------------------------------------------------------------------------------------------
 template <int DT, int BN, int EPI, bool GELU>
-static int launch_one(vtq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
-                      const float* bias, const float* gamma, int M, int N, int K, int accumulate,
-                      cudaStream_t st) {
+static int launch_1cta(vtq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
+                       const float* bias, const float* gamma, int M, int N, int K, int accumulate,
+                       cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_kernel<DT, BN, EPI, GELU>;
   static bool configured = false;  // per instantiation
@@ -286,6 +498,26 @@ static int launch_one(vtq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& t
   const int grid = num_tiles < ctx->num_sms ? num_tiles : ctx->num_sms;
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmO, bias, gamma, M, N, K, accumulate);
   VTQ_CHECK_LAUNCH(ctx, "gemm launch");
+  return VTQ_OK;
+}
+
+template <int DT, int BN, int EPI, bool GELU>
+static int launch_2cta(vtq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
+                       const float* bias, const float* gamma, int M, int N, int K, int accumulate,
+                       cudaStream_t st) {
+  using Cfg = Gemm2Cfg<BN>;
+  auto kern = gemm2_kernel<DT, BN, EPI, GELU>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return check_cuda(ctx, e, "gemm2: cudaFuncSetAttribute");
+    configured = true;
+  }
+  const int num_tiles = ((M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * ((N + BN - 1) / BN);
+  const int max_pairs = ctx->num_sms / 2;
+  const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;
+  kern<<<2 * pairs, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmO, bias, gamma, M, N, K, accumulate);
+  VTQ_CHECK_LAUNCH(ctx, "gemm2 launch");
   return VTQ_OK;
 }
 
@@ -307,9 +539,16 @@ int launch_gemm(vtq_ctx* ctx, const void* A, int64_t lda, const void* W, const f
                 "pointers must be 16-byte aligned");
   VTQ_CHECK_ARG(ctx, gamma == nullptr || reinterpret_cast<uintptr_t>(gamma) % 16 == 0, "gamma alignment");
 
-  // Wide N (QKV, fc1) uses 128x256 tiles; N=768 GEMMs use 128x128 tiles to cut wave quantisation.
-  const int BN = (N % 256 == 0 && N >= 1536) ? 256 : 128;
-  VTQ_CHECK_ARG(ctx, N % BN == 0 || N % 64 == 0, "N tiling");
+  static const bool force_1cta = [] {
+    const char* e = std::getenv("VTQ_GEMM_1CTA");
+    return e != nullptr && e[0] == '1';
+  }();
+  const bool two_cta = !force_1cta && M >= 2 * GEMM_BM;
+  // Tile width: 256 for the wide projections (QKV, fc1); N = 768 (attn.out, fc2, patch embed) splits into
+  // 4 x 192 under the CTA-pair kernel (504 pair-tiles on 74 pairs = 97 % wave efficiency; 3 x 256 gives 85 %).
+  int BN;
+  if (two_cta) BN = (N % 256 == 0 && N >= 1536) ? 256 : (N % 192 == 0 ? 192 : 128);
+  else BN = (N % 256 == 0 && N >= 1536) ? 256 : 128;
 
   CUtensorMap tmA, tmB, tmO;
   const CUtensorMapDataType dt16 = tm_dtype16(dtype);
@@ -323,7 +562,7 @@ int launch_gemm(vtq_ctx* ctx, const void* A, int64_t lda, const void* W, const f
   {
     uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
     uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
-    uint32_t box[2] = {GEMM_BK, static_cast<uint32_t>(BN)};
+    uint32_t box[2] = {GEMM_BK, static_cast<uint32_t>(two_cta ? BN / 2 : BN)};
     int rc = make_tensor_map(ctx, &tmB, dt16, 2, W, dims, strides, box);
     if (rc) return rc;
   }
@@ -337,18 +576,24 @@ int launch_gemm(vtq_ctx* ctx, const void* A, int64_t lda, const void* W, const f
   const int acc = epilogue == VTQ_EPI_BIAS_RESID_F32 ? 1 : 0;
   if (epilogue != VTQ_EPI_BIAS_RESID_F32) gamma = nullptr;
 
-#define VTQ_GEMM_DISPATCH(DTV, BNV)                                                                             \
-  switch (epilogue) {                                                                                           \
-    case VTQ_EPI_BIAS_H: return launch_one<DTV, BNV, EPI_H, false>(ctx, tmA, tmB, tmO, bias, gamma, M, N, K, 0, st); \
-    case VTQ_EPI_BIAS_GELU_H: return launch_one<DTV, BNV, EPI_H, true>(ctx, tmA, tmB, tmO, bias, gamma, M, N, K, 0, st); \
-    default: return launch_one<DTV, BNV, EPI_F32, false>(ctx, tmA, tmB, tmO, bias, gamma, M, N, K, acc, st);    \
+#define VTQ_GEMM_EPI(FN, DTV, BNV)                                                                          \
+  switch (epilogue) {                                                                                       \
+    case VTQ_EPI_BIAS_H: return FN<DTV, BNV, EPI_H, false>(ctx, tmA, tmB, tmO, bias, gamma, M, N, K, 0, st); \
+    case VTQ_EPI_BIAS_GELU_H: return FN<DTV, BNV, EPI_H, true>(ctx, tmA, tmB, tmO, bias, gamma, M, N, K, 0, st); \
+    default: return FN<DTV, BNV, EPI_F32, false>(ctx, tmA, tmB, tmO, bias, gamma, M, N, K, acc, st);        \
   }
-  if (dtype == VTQ_F16) {
-    if (BN == 256) { VTQ_GEMM_DISPATCH(DT_F16, 256) } else { VTQ_GEMM_DISPATCH(DT_F16, 128) }
+#define VTQ_GEMM_DT(FN, BNV)                                     \
+  if (dtype == VTQ_F16) { VTQ_GEMM_EPI(FN, DT_F16, BNV) } else { VTQ_GEMM_EPI(FN, DT_BF16, BNV) }
+  if (two_cta) {
+    if (BN == 256) { VTQ_GEMM_DT(launch_2cta, 256) }
+    if (BN == 192) { VTQ_GEMM_DT(launch_2cta, 192) }
+    VTQ_GEMM_DT(launch_2cta, 128)
   } else {
-    if (BN == 256) { VTQ_GEMM_DISPATCH(DT_BF16, 256) } else { VTQ_GEMM_DISPATCH(DT_BF16, 128) }
+    if (BN == 256) { VTQ_GEMM_DT(launch_1cta, 256) }
+    VTQ_GEMM_DT(launch_1cta, 128)
   }
-#undef VTQ_GEMM_DISPATCH
+#undef VTQ_GEMM_DT
+#undef VTQ_GEMM_EPI
 }
 
 }  // namespace vtq
