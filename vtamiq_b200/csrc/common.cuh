@@ -66,14 +66,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done = 0;
   uint32_t spins = 0;
   while (true) {
+    // try_wait with a suspend-time hint: the thread sleeps in hardware until the phase flips (or the hint
+    // expires) instead of burning issue slots that the co-resident working warps need
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
         "}\n"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(1000000u)
         : "memory");
     if (done) break;
     if (++spins > VTQ_SPIN_LIMIT) __trap();
