@@ -116,6 +116,13 @@ int vtq_gemm(vtq_ctx* ctx, const void* A, int64_t lda, const void* W, const floa
 int vtq_attention_fwd(vtq_ctx* ctx, const void* qkv, void* out, int n_seq, int S, int heads, int dtype,
                       void* stream);
 
+/* Diagnostics: same as vtq_attention_fwd, and CTA 0 writes clock64() stamps of its pipeline events into
+ * trace[3][512] (device memory, zero it first): row 0 = MMA issue thread (after every Q K^T / P V commit), rows 1,2 =
+ * softmax warpgroups A,B (7 events per key tile: wait S, S ready, S in registers, max done, prev P V retired,
+ * SFU turn acquired, P published; +1 per work item).  Used by scripts/attn_trace.py to attribute stalls; not part of the hot path. */
+int vtq_attention_fwd_trace(vtq_ctx* ctx, const void* qkv, void* out, int n_seq, int S, int heads, int dtype,
+                            long long* trace, void* stream);
+
 /* ---- K7: final LayerNorm of the quality token + difference ----------------------------------------
  * replaces encoder_norm on the used token (transformer.py:376,:634) and modules/vtamiq/vtamiq.py:104-111.
  * x [2*B][S][hidden] fp32; diff[b] = gamma * (LN(x[b][token]) - LN(x[B+b][token])); gamma may be NULL. */

@@ -110,3 +110,9 @@ extern "C" int vtq_attention_fwd(vtq_ctx* ctx, const void* qkv, void* out, int n
   if (!ctx) return VTQ_ERR_INVALID;
   return launch_attention(ctx, qkv, out, n_seq, S, heads, dtype, static_cast<cudaStream_t>(stream));
 }
+
+extern "C" int vtq_attention_fwd_trace(vtq_ctx* ctx, const void* qkv, void* out, int n_seq, int S, int heads,
+                                       int dtype, long long* trace, void* stream) {
+  if (!ctx) return VTQ_ERR_INVALID;
+  return launch_attention(ctx, qkv, out, n_seq, S, heads, dtype, static_cast<cudaStream_t>(stream), trace);
+}

@@ -1,7 +1,9 @@
 // K6 — fused multi-head self-attention, softmax(Q K^T / 8) V, head_dim 64, no mask.
 //
-// One CTA per (PAIR of 128-row query tiles, head, sequence); ref and dist sequences of the whole batch go through
-// one launch (sequence index = img * B + b).  The S x S score matrix lives only in TMEM / registers:
+// Persistent: one CTA per SM loops over work items = (sequence, head, PAIR of 128-row query tiles); ref and dist
+// sequences of the whole batch go through one launch (sequence index = img * B + b).  All pipelines (Q double
+// buffer, K/V ring, S/P/O hand-offs) run across work-item boundaries, so loads and Q K^T of the next item overlap
+// the tail of the current one.  The S x S score matrix lives only in TMEM / registers:
 //   warp 0      TMA producer : both Q tiles once, then K/V tiles (128 keys x 64) through a 3-deep smem ring that
 //                              the two query tiles share
 //   warp 1      MMA issuer   : S_t = Q_t K^T (tcgen05.mma M128 N128 K16 x4, both operands K-major) and
@@ -29,44 +31,57 @@ constexpr int ATT_THREADS = 3 * 128;  // warpgroup 0: TMA + MMA warps (+2 idle),
 constexpr int ATT_TILE_BYTES = 128 * ATT_D * 2;  // 16 KB: a 128-row x 64 x 16-bit tile
 constexpr int ATT_KV_STAGES = 3;
 constexpr int ATT_P_BYTES = ATT_BQ * ATT_BKV * 2;  // 32 KB per query tile
-constexpr int ATT_SMEM_BYTES = ATT_TILE_BYTES * (2 + 2 * ATT_KV_STAGES) + 2 * ATT_P_BYTES + 256;
+constexpr int ATT_SMEM_BYTES = ATT_TILE_BYTES * (4 + 2 * ATT_KV_STAGES) + 2 * ATT_P_BYTES + 256;
 static_assert(ATT_SMEM_BYTES <= 227 * 1024, "smem budget");
+constexpr int ATT_XU_RELEASE_CHUNK = 11;  // of 16 eight-key chunks per row
 constexpr uint32_t ATT_TMEM_COLS = 512;
 constexpr uint32_t ATT_TMEM_S = 0;    // + t * 128
 constexpr uint32_t ATT_TMEM_O = 256;  // + t * 64
 
+// Diagnostics (vtq_attention_fwd_trace): CTA 0 records clock64() at pipeline events; slot layout
+// trace[role * 512 + event_index], role 0 = MMA thread, 1 = softmax A (warp 4 lane 0), 2 = softmax B.
+#define ATT_TRACE(role, idx)                                                                     \
+  do {                                                                                           \
+    if (trace != nullptr && blockIdx.x == 0 && (idx) < 512) trace[(role) * 512 + (idx)] = clock64(); \
+  } while (0)
+
 template <int DT>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
     attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, int S,
-                     int heads) {
+                     int heads, int n_seq, long long* __restrict__ trace) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B-swizzle atoms need a 1024 B aligned base
-  uint8_t* sQ = smem;                                  // [2 tiles]
-  uint8_t* sK = sQ + 2 * ATT_TILE_BYTES;               // [stages]
+  uint8_t* sQ = smem;                                  // [2 buffers][2 tiles]
+  uint8_t* sK = sQ + 4 * ATT_TILE_BYTES;               // [stages]
   uint8_t* sV = sK + ATT_KV_STAGES * ATT_TILE_BYTES;   // [stages]
-  uint8_t* sP = sV + ATT_KV_STAGES * ATT_TILE_BYTES;   // [2 tiles]; reused as output staging at the end
+  uint8_t* sP = sV + ATT_KV_STAGES * ATT_TILE_BYTES;   // [2 tiles]; also the output staging of each work item
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * ATT_P_BYTES);
-  uint64_t* q_full = bars;            // 1
-  uint64_t* kv_full = bars + 1;       // [3]
-  uint64_t* kv_empty = bars + 4;      // [3]
-  uint64_t* s_full = bars + 7;        // [2] S_t(j) complete                      (MMA commit)
-  uint64_t* s_free = bars + 9;        // [2] S_t(j) copied to registers           (128 arrivals)
-  uint64_t* p_full = bars + 11;       // [2] P_t(j) in smem, O_t rescaled         (128 arrivals)
-  uint64_t* pv_done = bars + 13;      // [2] O_t += P_t(j) V(j) complete          (MMA commit)
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* q_full = bars;            // [2] Q pair of a work item landed            (TMA tx)
+  uint64_t* q_empty = bars + 2;       // [2] all Q K^T of that work item retired     (MMA commit)
+  uint64_t* kv_full = bars + 4;       // [3]
+  uint64_t* kv_empty = bars + 7;      // [3]
+  uint64_t* s_full = bars + 10;       // [2] S_t(n) complete                         (MMA commit)
+  uint64_t* s_free = bars + 12;       // [2] S_t(n) copied to registers              (128 arrivals)
+  uint64_t* p_full = bars + 14;       // [2] P_t(n) in smem, O_t rescaled            (128 arrivals)
+  uint64_t* pv_done = bars + 16;      // [2] O_t += P_t(n) V complete                (MMA commit)
+  uint64_t* o_free = bars + 18;       // [2] O_t of a finished work item read out    (128 arrivals)
+  uint64_t* xu_turn = bars + 20;      // [2] exponential phases of the two groups alternate (4 warp arrivals)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 22);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * (2 * ATT_BQ);
-  const int head = blockIdx.y;
-  const int seq = blockIdx.z;
   const int hidden = heads * ATT_D;
   const int nkv = (S + ATT_BKV - 1) / ATT_BKV;
+  const int nqp = (S + 2 * ATT_BQ - 1) / (2 * ATT_BQ);  // query-tile pairs per (sequence, head)
+  const int n_items = nqp * heads * n_seq;               // work item = (seq, head, query pair), pair fastest
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmO);
-    mbar_init(q_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&q_full[b], 1);
+      mbar_init(&q_empty[b], 1);
+    }
     for (int s = 0; s < ATT_KV_STAGES; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
@@ -76,6 +91,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
       mbar_init(&s_free[t], 128);
       mbar_init(&p_full[t], 128);
       mbar_init(&pv_done[t], 1);
+      mbar_init(&o_free[t], 128);
+      mbar_init(&xu_turn[t], 4);
     }
     fence_barrier_init();
   }
@@ -87,75 +104,104 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-  if (warp == 0) {
-    // ------------------------------- TMA producer -------------------------------
-    if (lane == 0) {
-      mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
-      tma_load_3d(sQ, &tmQKV, q_full, head * ATT_D, q0, seq);
-      tma_load_3d(sQ + ATT_TILE_BYTES, &tmQKV, q_full, head * ATT_D, q0 + ATT_BQ, seq);
-      for (int j = 0; j < nkv; ++j) {
-        const int st = j % ATT_KV_STAGES;
-        const uint32_t ph = (j / ATT_KV_STAGES) & 1;
-        mbar_wait(&kv_empty[st], ph ^ 1);
-        mbar_expect_tx(&kv_full[st], 2 * ATT_TILE_BYTES);
-        tma_load_3d(sK + st * ATT_TILE_BYTES, &tmQKV, &kv_full[st], hidden + head * ATT_D, j * ATT_BKV, seq);
-        tma_load_3d(sV + st * ATT_TILE_BYTES, &tmQKV, &kv_full[st], 2 * hidden + head * ATT_D, j * ATT_BKV, seq);
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ------------------------------- MMA issuer ---------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = umma_idesc_f16(DT, ATT_BQ, ATT_BKV, 0, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_f16(DT, ATT_BQ, ATT_D, 0, 1);  // B (=V) is MN-major
-
-      auto issue_qk = [&](int t, int j) {
-        const uint64_t dQ = umma_smem_desc(smem_u32(sQ + t * ATT_TILE_BYTES), 16, 1024);
-        const uint64_t dK = umma_smem_desc(smem_u32(sK + (j % ATT_KV_STAGES) * ATT_TILE_BYTES), 16, 1024);
-#pragma unroll
-        for (int k = 0; k < ATT_D / 16; ++k)
-          umma_f16_ss(tmem_base + ATT_TMEM_S + t * 128, dQ + uint64_t(k * 2), dK + uint64_t(k * 2), idesc_qk,
-                      k ? 1u : 0u);
-        umma_commit(&s_full[t]);
-      };
-      auto issue_pv = [&](int t, int j) {
-        // O_t (+)= P_t(j) V(j): 8 k-steps of 16 keys.  P: two 64-key K-major blocks of 16 KB.  V: rows = keys,
-        // 128 B apart, 8-key groups 1024 B apart -> one k-step advances the start address by 2048 B.
-        const uint32_t aP = smem_u32(sP + t * ATT_P_BYTES);
-        const uint32_t aV = smem_u32(sV + (j % ATT_KV_STAGES) * ATT_TILE_BYTES);
-#pragma unroll
-        for (int kk = 0; kk < ATT_BKV / 16; ++kk) {
-          const uint64_t dP = umma_smem_desc(aP + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
-          const uint64_t dV = umma_smem_desc(aV + kk * 2048, 1024, 1024);
-          umma_f16_ss(tmem_base + ATT_TMEM_O + t * 64, dP, dV, idesc_pv, (j | kk) ? 1u : 0u);
-        }
-        umma_commit(&pv_done[t]);
-      };
-
-      mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      issue_qk(0, 0);
-      issue_qk(1, 0);
-      for (int j = 0; j < nkv; ++j) {
-        const bool more = j + 1 < nkv;
-        if (more) mbar_wait(&kv_full[(j + 1) % ATT_KV_STAGES], ((j + 1) / ATT_KV_STAGES) & 1);
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          if (more) {  // next score tile as soon as the softmax group has pulled S_t(j) into registers
-            mbar_wait(&s_free[t], j & 1);
-            tc_fence_after();
-            issue_qk(t, j + 1);
+    if (warp == 0) {
+      // ------------------------------- TMA producer -------------------------------
+      if (lane == 0) {
+        uint32_t it = 0, kvc = 0;
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+          const int qp = w % nqp;
+          const int head = (w / nqp) % heads;
+          const int seq = w / (nqp * heads);
+          const int q0 = qp * (2 * ATT_BQ);
+          const uint32_t qb = it & 1;
+          mbar_wait(&q_empty[qb], ((it >> 1) & 1) ^ 1);
+          mbar_expect_tx(&q_full[qb], 2 * ATT_TILE_BYTES);
+          tma_load_3d(sQ + (2 * qb) * ATT_TILE_BYTES, &tmQKV, &q_full[qb], head * ATT_D, q0, seq);
+          tma_load_3d(sQ + (2 * qb + 1) * ATT_TILE_BYTES, &tmQKV, &q_full[qb], head * ATT_D, q0 + ATT_BQ, seq);
+          for (int j = 0; j < nkv; ++j, ++kvc) {
+            const uint32_t st = kvc % ATT_KV_STAGES;
+            mbar_wait(&kv_empty[st], ((kvc / ATT_KV_STAGES) & 1) ^ 1);
+            mbar_expect_tx(&kv_full[st], 2 * ATT_TILE_BYTES);
+            tma_load_3d(sK + st * ATT_TILE_BYTES, &tmQKV, &kv_full[st], hidden + head * ATT_D, j * ATT_BKV, seq);
+            tma_load_3d(sV + st * ATT_TILE_BYTES, &tmQKV, &kv_full[st], 2 * hidden + head * ATT_D, j * ATT_BKV, seq);
           }
-          mbar_wait(&p_full[t], j & 1);
-          tc_fence_after();
-          issue_pv(t, j);
         }
-        umma_commit(&kv_empty[j % ATT_KV_STAGES]);  // K(j), V(j) no longer needed once everything above retires
       }
+      __syncwarp();
+    } else if (warp == 1) {
+      // ------------------------------- MMA issuer ---------------------------------
+      if (lane == 0) {
+        constexpr uint32_t idesc_qk = umma_idesc_f16(DT, ATT_BQ, ATT_BKV, 0, 0);
+        constexpr uint32_t idesc_pv = umma_idesc_f16(DT, ATT_BQ, ATT_D, 0, 1);  // B (=V) is MN-major
+        uint32_t n_s[2] = {0, 0};  // score tiles issued per query tile (global over work items)
+        uint32_t n_p[2] = {0, 0};  // P V products issued per query tile
+        int tr = 0;
+
+        auto issue_qk = [&](int t, uint32_t qb, uint32_t kv_idx) {
+          if (n_s[t] > 0) {  // the softmax group must have pulled the previous S_t into registers
+            mbar_wait(&s_free[t], (n_s[t] - 1) & 1);
+            tc_fence_after();
+          }
+          const uint64_t dQ = umma_smem_desc(smem_u32(sQ + (2 * qb + t) * ATT_TILE_BYTES), 16, 1024);
+          const uint64_t dK = umma_smem_desc(smem_u32(sK + (kv_idx % ATT_KV_STAGES) * ATT_TILE_BYTES), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < ATT_D / 16; ++k)
+            umma_f16_ss(tmem_base + ATT_TMEM_S + t * 128, dQ + uint64_t(k * 2), dK + uint64_t(k * 2), idesc_qk,
+                        k ? 1u : 0u);
+          umma_commit(&s_full[t]);
+          ++n_s[t];
+          ATT_TRACE(0, tr++);
+        };
+        auto issue_pv = [&](int t, uint32_t kv_idx, bool first) {
+          // O_t (+)= P_t V: 8 k-steps of 16 keys.  P: two 64-key K-major blocks of 16 KB.  V: rows = keys, 128 B
+          // apart, 8-key groups 1024 B apart -> one k-step advances the start address by 2048 B.
+          mbar_wait(&p_full[t], n_p[t] & 1);
+          tc_fence_after();
+          const uint32_t aP = smem_u32(sP + t * ATT_P_BYTES);
+          const uint32_t aV = smem_u32(sV + (kv_idx % ATT_KV_STAGES) * ATT_TILE_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < ATT_BKV / 16; ++kk) {
+            const uint64_t dP = umma_smem_desc(aP + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
+            const uint64_t dV = umma_smem_desc(aV + kk * 2048, 1024, 1024);
+            umma_f16_ss(tmem_base + ATT_TMEM_O + t * 64, dP, dV, idesc_pv, (!first || kk) ? 1u : 0u);
+          }
+          umma_commit(&pv_done[t]);
+          ++n_p[t];
+          ATT_TRACE(0, tr++);
+        };
+
+        uint32_t it = 0, kvc = 0;
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+          const uint32_t qb = it & 1;
+          mbar_wait(&q_full[qb], (it >> 1) & 1);
+          mbar_wait(&kv_full[kvc % ATT_KV_STAGES], (kvc / ATT_KV_STAGES) & 1);
+          tc_fence_after();
+          issue_qk(0, qb, kvc);
+          issue_qk(1, qb, kvc);
+          for (int j = 0; j < nkv; ++j) {
+            const bool more = j + 1 < nkv;
+            const uint32_t kn = kvc + j + 1;
+            if (more) {
+              mbar_wait(&kv_full[kn % ATT_KV_STAGES], (kn / ATT_KV_STAGES) & 1);
+              tc_fence_after();
+            }
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              if (more) issue_qk(t, qb, kn);  // next score tile runs underneath this tile's exponentials
+              if (j == 0 && it > 0) {         // the first P V of a work item overwrites O_t: previous O read out?
+                mbar_wait(&o_free[t], (it - 1) & 1);
+                tc_fence_after();
+              }
+              issue_pv(t, kvc + j, j == 0);
+            }
+            if (!more) umma_commit(&q_empty[qb]);            // every Q K^T of this work item has been issued
+            umma_commit(&kv_empty[(kvc + j) % ATT_KV_STAGES]);  // K(j), V(j) free once everything above retires
+          }
+          kvc += nkv;
+        }
+      }
+      __syncwarp();
     }
-    __syncwarp();
-  }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     // ------------------------------- softmax / correction / output --------------
@@ -167,125 +213,170 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
     const uint32_t tO = t_lane + ATT_TMEM_O + t * 64;
     const uint32_t swz = static_cast<uint32_t>(row & 7);
     const uint32_t p_row = smem_u32(sP + t * ATT_P_BYTES) + row * 128;
+    uint8_t* stage_out = sP + t * ATT_P_BYTES + lane_grp * 4096;  // == this warp's 32 rows of P block 0
+    const uint32_t o_row = smem_u32(stage_out) + lane * 128;
+    const uint32_t oswz = static_cast<uint32_t>(lane & 7);
     const float c = 0.125f * 1.44269504088896340736f;  // (1/sqrt(64)) * log2(e)
     const f32x2 c2 = f2_pack(c, c);
 
-    float m = -INFINITY;  // reference max (raw score domain) that P and O are currently scaled by
-    float l = 0.f;        // running sum of exp
-    for (int j = 0; j < nkv; ++j) {
-      mbar_wait(&s_full[t], j & 1);
-      tc_fence_after();
-      uint32_t r[128];
-      tmem_ld32(tS + 0, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-      tmem_ld32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
-      tmem_ld32(tS + 64, *reinterpret_cast<uint32_t(*)[32]>(&r[64]));
-      tmem_ld32(tS + 96, *reinterpret_cast<uint32_t(*)[32]>(&r[96]));
-      tmem_wait_ld();
-      tc_fence_before();
-      mbar_arrive(&s_free[t]);  // S_t may be overwritten by Q_t K(j+1)^T from here on
+    uint32_t n = 0;  // score tiles consumed by this warpgroup (global over work items)
+    int tr = 0;
+    const bool tracer = (lane == 0) && (lane_grp == 0);
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+      const int qp = w % nqp;
+      const int head = (w / nqp) % heads;
+      const int seq = w / (nqp * heads);
+      const int q0 = qp * (2 * ATT_BQ);
+      // the previous work item's output store must have finished reading the staging rows (they alias P_t)
+      if (lane == 0) tma_wait_group_read<0>();
+      __syncwarp();
 
-      const int kv_valid = S - j * ATT_BKV;  // keys of this tile that exist (>= 1)
-      if (kv_valid < ATT_BKV) {              // CTA-uniform: only the last key tile of a ragged sequence
-#pragma unroll
-        for (int e = 0; e < 128; ++e)
-          if (e >= kv_valid) r[e] = 0xff800000u;  // -inf -> exp2 gives exactly 0
-      }
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-      for (int e = 0; e < 128; e += 8) {
-        mx0 = fmax3(mx0, __uint_as_float(r[e + 0]), __uint_as_float(r[e + 1]));
-        mx1 = fmax3(mx1, __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
-        mx2 = fmax3(mx2, __uint_as_float(r[e + 4]), __uint_as_float(r[e + 5]));
-        mx3 = fmax3(mx3, __uint_as_float(r[e + 6]), __uint_as_float(r[e + 7]));
-      }
-      float m_new = fmaxf(fmaxf(m, fmax3(mx0, mx1, mx2)), mx3);
-      // Lazy rescale: keep the old reference max while the true max grew by < 2^8 in the exp2 domain — P then
-      // stays <= 256 (exact in fp16/bf16 range, fp32 sums) and O needs no correction.  First tile: m = -inf.
-      if ((m_new - m) * c <= 8.0f) m_new = m;
-
-      if (j > 0) {
-        // P_t(j-1) V(j-1) must have retired before P_t is overwritten or O_t is touched
-        mbar_wait(&pv_done[t], (j - 1) & 1);
+      float m = -INFINITY;  // reference max (raw score domain) that P and O are currently scaled by
+      float l = 0.f;        // running sum of exp
+      bool s_ok = false;    // early probe of the next S tile (issued before the exponentials of the current one)
+      for (int j = 0; j < nkv; ++j, ++n) {
+        if (tracer) ATT_TRACE(1 + t, tr++);  // 0: start waiting for S
+        if (!s_ok) mbar_wait(&s_full[t], n & 1);
         tc_fence_after();
-        if (__any_sync(0xffffffffu, m_new != m)) {
-          const float alpha = ex2_approx((m - m_new) * c);
-          l *= alpha;
+        if (tracer) ATT_TRACE(1 + t, tr++);  // 1: S ready
+        uint32_t r[128];
+        tmem_ld32(tS + 0, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+        tmem_ld32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+        tmem_ld32(tS + 64, *reinterpret_cast<uint32_t(*)[32]>(&r[64]));
+        tmem_ld32(tS + 96, *reinterpret_cast<uint32_t(*)[32]>(&r[96]));
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive(&s_free[t]);  // S_t may be overwritten by the next Q_t K^T from here on
+        if (tracer) ATT_TRACE(1 + t, tr++);  // 2: S in registers
+        // probe the two hand-offs needed before the exponentials now; their round trips hide under the row max
+        const uint32_t turn_parity = (t == 0) ? ((n & 1) ^ 1) : (n & 1);
+        const bool pv_ok = (j == 0) || mbar_test(&pv_done[t], (n - 1) & 1);
+        const bool turn_ok = mbar_test(&xu_turn[t], turn_parity);
+
+        const int kv_valid = S - j * ATT_BKV;  // keys of this tile that exist (>= 1)
+        if (kv_valid < ATT_BKV) {              // CTA-uniform: only the last key tile of a ragged sequence
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            uint32_t o[32];
-            tmem_ld32(tO + hh * 32, o);
-            tmem_wait_ld();
+          for (int ch = 0; ch < 4; ++ch) {
+            if (kv_valid < (ch + 1) * 32) {    // uniform: chunks entirely inside the sequence are skipped
 #pragma unroll
-            for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-            tmem_st32(tO + hh * 32, o);
+              for (int e = ch * 32; e < ch * 32 + 32; ++e)
+                if (e >= kv_valid) r[e] = 0xff800000u;  // -inf -> exp2 gives exactly 0
+            }
           }
-          tmem_wait_st();
         }
-      }
-      m = m_new;
-      const float nmc = -m_new * c;
-      const f32x2 nmc2 = f2_pack(nmc, nmc);
-
-      // p = exp2(s*c - m*c): packed FFMA2 + MUFU.EX2, packed partial sums, 16-bit P into swizzled smem
-      f32x2 sum_a = 0ull, sum_b = 0ull;
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int cc = 0; cc < ATT_BKV / 8; ++cc) {  // 8 keys = one 16-byte chunk of this row
-        uint32_t pk[4];
-#pragma unroll
-        for (int q = 0; q < 4; q += 2) {
-          const int e = cc * 8 + q * 2;
-          float t0, t1, t2, t3;
-          f2_unpack(f2_fma(f2_pack(__uint_as_float(r[e]), __uint_as_float(r[e + 1])), c2, nmc2), t0, t1);
-          f2_unpack(f2_fma(f2_pack(__uint_as_float(r[e + 2]), __uint_as_float(r[e + 3])), c2, nmc2), t2, t3);
-          const float p0 = ex2_approx(t0), p1 = ex2_approx(t1), p2 = ex2_approx(t2), p3 = ex2_approx(t3);
-          sum_a = f2_add(sum_a, f2_pack(p0, p1));
-          sum_b = f2_add(sum_b, f2_pack(p2, p3));
-          pk[q] = pack2<DT>(p0, p1);
-          pk[q + 1] = pack2<DT>(p2, p3);
+        for (int e = 0; e < 128; e += 8) {
+          mx0 = fmax3(mx0, __uint_as_float(r[e + 0]), __uint_as_float(r[e + 1]));
+          mx1 = fmax3(mx1, __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
+          mx2 = fmax3(mx2, __uint_as_float(r[e + 4]), __uint_as_float(r[e + 5]));
+          mx3 = fmax3(mx3, __uint_as_float(r[e + 6]), __uint_as_float(r[e + 7]));
         }
-        const uint32_t blk = p_row + (cc >> 3) * 16384;  // 64-key K-major block
-        st_shared_v4(blk + ((static_cast<uint32_t>(cc & 7) ^ swz) << 4), pk[0], pk[1], pk[2], pk[3]);
-      }
-      {
-        float s0, s1;
-        f2_unpack(f2_add(sum_a, sum_b), s0, s1);
-        l += s0 + s1;
-      }
-      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      tc_fence_before();
-      mbar_arrive(&p_full[t]);
-    }
+        float m_new = fmaxf(fmaxf(m, fmax3(mx0, mx1, mx2)), mx3);
+        // Lazy rescale: keep the old reference max while the true max grew by < 2^8 in the exp2 domain — P then
+        // stays <= 256 (exact in fp16/bf16 range, fp32 sums) and O needs no correction.  First tile: m = -inf.
+        if ((m_new - m) * c <= 8.0f) m_new = m;
 
-    // output: O / l -> 16 bit -> staging (this tile's P buffer is free once the last P V retired) -> TMA store
-    mbar_wait(&pv_done[t], (nkv - 1) & 1);
-    tc_fence_after();
-    const float inv_l = 1.0f / l;
-    uint8_t* stage_out = sP + t * ATT_P_BYTES + lane_grp * 4096;
-    const uint32_t o_row = smem_u32(stage_out) + lane * 128;
-    const uint32_t oswz = static_cast<uint32_t>(lane & 7);
+        if (tracer) ATT_TRACE(1 + t, tr++);  // 3: row max done
+        if (j > 0) {
+          // P_t V of the previous tile must have retired before P_t is overwritten or O_t is touched
+          if (!pv_ok) mbar_wait(&pv_done[t], (n - 1) & 1);
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, m_new != m)) {
+            const float alpha = ex2_approx((m - m_new) * c);
+            l *= alpha;
 #pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      uint32_t o[32];
-      tmem_ld32(tO + hh * 32, o);
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t o[32];
+              tmem_ld32(tO + hh * 32, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+              tmem_st32(tO + hh * 32, o);
+            }
+            tmem_wait_st();
+          }
+        }
+        if (tracer) ATT_TRACE(1 + t, tr++);  // 4: previous P V retired (+ rescale)
+        m = m_new;
+        const float nmc = -m_new * c;
+        const f32x2 nmc2 = f2_pack(nmc, nmc);
+
+        // The two softmax groups take turns on the SFU (16 ex2/clk/SM is the binding pipe): while one group
+        // runs its 128 exponentials per thread, the other does its latency-bound part (S load, max, hand-offs).
+        if (!turn_ok) mbar_wait(&xu_turn[t], turn_parity);
+        if (tracer) ATT_TRACE(1 + t, tr++);  // 5: SFU turn acquired
+        s_ok = (j + 1 < nkv) && mbar_test(&s_full[t], (n + 1) & 1);  // consumed at the top of the next tile
+        // p = exp2(s*c - m*c): packed FFMA2 + MUFU.EX2, packed partial sums, 16-bit P into swizzled smem
+        f32x2 sum_a = 0ull, sum_b = 0ull;
+#pragma unroll
+        for (int cc = 0; cc < ATT_BKV / 8; ++cc) {  // 8 keys = one 16-byte chunk of this row
+          uint32_t pk[4];
+#pragma unroll
+          for (int q = 0; q < 4; q += 2) {
+            const int e = cc * 8 + q * 2;
+            float t0, t1, t2, t3;
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(r[e]), __uint_as_float(r[e + 1])), c2, nmc2), t0, t1);
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(r[e + 2]), __uint_as_float(r[e + 3])), c2, nmc2), t2, t3);
+            const float p0 = ex2_approx(t0), p1 = ex2_approx(t1), p2 = ex2_approx(t2), p3 = ex2_approx(t3);
+            sum_a = f2_add(sum_a, f2_pack(p0, p1));
+            sum_b = f2_add(sum_b, f2_pack(p2, p3));
+            pk[q] = pack2<DT>(p0, p1);
+            pk[q + 1] = pack2<DT>(p2, p3);
+          }
+          const uint32_t blk = p_row + (cc >> 3) * 16384;  // 64-key K-major block
+          st_shared_v4(blk + ((static_cast<uint32_t>(cc & 7) ^ swz) << 4), pk[0], pk[1], pk[2], pk[3]);
+          if (cc == ATT_XU_RELEASE_CHUNK) {
+            // hand the SFU to the other group about one barrier wake-up latency before this group's last
+            // exponentials issue
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&xu_turn[t ^ 1]);
+          }
+        }
+        {
+          float s0, s1;
+          f2_unpack(f2_add(sum_a, sum_b), s0, s1);
+          l += s0 + s1;
+        }
+        fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        tc_fence_before();
+        mbar_arrive(&p_full[t]);
+        if (tracer) ATT_TRACE(1 + t, tr++);  // 6: P published
+      }
+
+      // output: O / l -> 16 bit -> staging (P_t is free once the last P V retired) -> TMA store
+      mbar_wait(&pv_done[t], (n - 1) & 1);
+      tc_fence_after();
+      uint32_t o0[32], o1[32];
+      tmem_ld32(tO, o0);
+      tmem_ld32(tO + 32, o1);
       tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(&o_free[t]);  // the next work item's first P V may overwrite O_t
+      const float inv_l = __frcp_rn(l);
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
-        float v[8];
+        float v[8], u[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(o[8 * jj + e]) * inv_l;
-        const uint32_t chunk = static_cast<uint32_t>(hh * 4 + jj);
-        st_shared_v4(o_row + ((chunk ^ oswz) << 4), pack2<DT>(v[0], v[1]), pack2<DT>(v[2], v[3]),
+        for (int e = 0; e < 8; ++e) {
+          v[e] = __uint_as_float(o0[8 * jj + e]) * inv_l;
+          u[e] = __uint_as_float(o1[8 * jj + e]) * inv_l;
+        }
+        st_shared_v4(o_row + ((static_cast<uint32_t>(jj) ^ oswz) << 4), pack2<DT>(v[0], v[1]), pack2<DT>(v[2], v[3]),
                      pack2<DT>(v[4], v[5]), pack2<DT>(v[6], v[7]));
+        st_shared_v4(o_row + ((static_cast<uint32_t>(4 + jj) ^ oswz) << 4), pack2<DT>(u[0], u[1]),
+                     pack2<DT>(u[2], u[3]), pack2<DT>(u[4], u[5]), pack2<DT>(u[6], u[7]));
       }
+      fence_proxy_async_smem();
+      __syncwarp();
+      const int out_row0 = q0 + t * ATT_BQ + lane_grp * 32;
+      if (lane == 0 && out_row0 < S) {
+        tma_store_3d(&tmO, stage_out, head * ATT_D, out_row0, seq);  // rows >= S are clipped by the tensor map
+        tma_commit_group();
+      }
+      if (tracer) ATT_TRACE(1 + t, tr++);  // 7: work item output issued
     }
-    fence_proxy_async_smem();
-    __syncwarp();
-    const int out_row0 = q0 + t * ATT_BQ + lane_grp * 32;
-    if (lane == 0 && out_row0 < S) {
-      tma_store_3d(&tmO, stage_out, head * ATT_D, out_row0, seq);  // rows >= S are clipped by the tensor map
-      tma_commit_group();
-      tma_wait_group<0>();
-    }
+    if (lane == 0) tma_wait_group<0>();
   }
 
   tc_fence_before();
@@ -294,10 +385,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
 }
 
 int launch_attention(vtq_ctx* ctx, const void* qkv, void* out, int n_seq, int S, int heads, int dtype,
-                     cudaStream_t st) {
+                     cudaStream_t st, long long* trace) {
   VTQ_CHECK_ARG(ctx, qkv && out, "null pointer");
   VTQ_CHECK_ARG(ctx, n_seq >= 1 && S >= 1 && heads >= 1, "empty problem");
-  VTQ_CHECK_ARG(ctx, n_seq <= 65535 && heads <= 65535, "grid limits: n_seq, heads <= 65535");
   VTQ_CHECK_ARG(ctx, dtype == VTQ_F16 || dtype == VTQ_BF16, "dtype must be VTQ_F16 or VTQ_BF16");
   VTQ_CHECK_ARG(ctx, (reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out)) % 16 == 0,
                 "pointers must be 16-byte aligned");
@@ -318,7 +408,9 @@ int launch_attention(vtq_ctx* ctx, const void* qkv, void* out, int n_seq, int S,
     int rc = make_tensor_map(ctx, &tmO, dt16, 3, out, dims, strides, box);
     if (rc) return rc;
   }
-  dim3 grid((S + 2 * ATT_BQ - 1) / (2 * ATT_BQ), heads, n_seq);
+  const long long n_items = static_cast<long long>((S + 2 * ATT_BQ - 1) / (2 * ATT_BQ)) * heads * n_seq;
+  VTQ_CHECK_ARG(ctx, n_items < (1ll << 30), "too many work items");
+  dim3 grid(static_cast<unsigned>(n_items < ctx->num_sms ? n_items : ctx->num_sms));
   static bool configured[2] = {false, false};
   if (dtype == VTQ_F16) {
     if (!configured[0]) {
@@ -327,7 +419,7 @@ int launch_attention(vtq_ctx* ctx, const void* qkv, void* out, int n_seq, int S,
       if (e != cudaSuccess) return check_cuda(ctx, e, "attention: cudaFuncSetAttribute");
       configured[0] = true;
     }
-    attention_kernel<DT_F16><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tmQKV, tmO, S, heads);
+    attention_kernel<DT_F16><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tmQKV, tmO, S, heads, n_seq, trace);
   } else {
     if (!configured[1]) {
       cudaError_t e = cudaFuncSetAttribute(attention_kernel<DT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -335,7 +427,7 @@ int launch_attention(vtq_ctx* ctx, const void* qkv, void* out, int n_seq, int S,
       if (e != cudaSuccess) return check_cuda(ctx, e, "attention: cudaFuncSetAttribute");
       configured[1] = true;
     }
-    attention_kernel<DT_BF16><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tmQKV, tmO, S, heads);
+    attention_kernel<DT_BF16><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tmQKV, tmO, S, heads, n_seq, trace);
   }
   VTQ_CHECK_LAUNCH(ctx, "attention launch");
   return VTQ_OK;

@@ -82,6 +82,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Non-blocking phase probe.  A satisfied mbar_wait still costs a ~100-200 cycle round trip to the barrier unit;
+// issuing the probe early and consuming its result after independent work hides that latency.
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // proxies / fences
 // ------------------------------------------------------------------------------------------
