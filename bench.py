@@ -333,6 +333,11 @@ def run_gpu_arm(args):
             "gemm_fc1": 2.0 * rows * HIDDEN * MLP,
             "gemm_fc2": 2.0 * rows * HIDDEN * MLP,
             "attention": 4.0 * (2 * B) * S * S * HIDDEN,
+            # last block, quality-token rows only (2B rows); attention: one 256-row granule against all S keys
+            "gemm_out_tok": 2.0 * (2 * B) * HIDDEN * HIDDEN,
+            "gemm_fc1_tok": 2.0 * (2 * B) * HIDDEN * MLP,
+            "gemm_fc2_tok": 2.0 * (2 * B) * HIDDEN * MLP,
+            "attention_tok": 4.0 * (2 * B) * min(256, S) * S * HIDDEN,
         }
         breakdown = {}
         step_ms = sum(sum(v) for v in agg.values()) / nprof
@@ -354,6 +359,8 @@ def run_gpu_arm(args):
             "peak_src": f"MEASURED_PEAKS.json ({pk['src']}): bf16 sustained {pk['sustained']}, burst {pk['burst']}; "
                         "kernel timed inside a long step -> sustained",
             "flops_per_step": g_fl, "avg_ms_per_step": round(g_ms, 3), "share_of_step": round(g_ms / step_ms, 4),
+            "note": "executed FLOPs of the full-row projection launches (the last block's token-row launches are "
+                    "listed separately under kernels as *_tok)",
             "traffic": None,
         }
 

@@ -98,9 +98,10 @@ int vtq_embed_assemble(vtq_ctx* ctx, const float* proj, const float* pos, const 
                        int hidden, float* x, int32_t* pos_idx, int32_t* scale_idx, void* stream);
 
 /* ---- K4: LayerNorm, fp32 rows -> 16-bit rows ----------------------------------------------------
- * replaces nn.LayerNorm(768, eps=1e-6) at transformer.py:253-254,:276,:281 (encoder_norm: see K7). */
-int vtq_layernorm(vtq_ctx* ctx, const float* x, const float* weight, const float* bias, float eps, int64_t rows,
-                  int hidden, void* out16, int dtype, void* stream);
+ * replaces nn.LayerNorm(768, eps=1e-6) at transformer.py:253-254,:276,:281 (encoder_norm: see K7).
+ * Row r is read at x + r * x_stride (elements; 0 = hidden) and written densely at out16 + r * hidden. */
+int vtq_layernorm(vtq_ctx* ctx, const float* x, int64_t x_stride, const float* weight, const float* bias, float eps,
+                  int64_t rows, int hidden, void* out16, int dtype, void* stream);
 
 /* ---- K3/K5: dense projection on tcgen05 ----------------------------------------------------------
  * out = epilogue(A[M][K] * W[N][K]^T + bias[N]).  A, W 16-bit (lda/ldw = K unless lda given), fp32 accumulate
@@ -112,8 +113,10 @@ int vtq_gemm(vtq_ctx* ctx, const void* A, int64_t lda, const void* W, const floa
 
 /* ---- K6: fused multi-head self-attention -----------------------------------------------------------
  * replaces transformer.py:158-166: softmax(Q K^T / sqrt(64)) V per (sequence, head), never materialising S x S.
- * qkv [n_seq*S][3*heads*64] 16-bit rows = [q | k | v];  out [n_seq*S][heads*64] 16-bit (head-concatenated). */
-int vtq_attention_fwd(vtq_ctx* ctx, const void* qkv, void* out, int n_seq, int S, int heads, int dtype,
+ * qkv [n_seq*S][3*heads*64] 16-bit rows = [q | k | v];  out [n_seq*S][heads*64] 16-bit (head-concatenated).
+ * q_rows: 0 = all S query rows; otherwise only query rows [0, q_rows) of every sequence are produced (rounded up
+ * to the 256-row work granule) — the last encoder block needs the prefix tokens only (transformer.py:634). */
+int vtq_attention_fwd(vtq_ctx* ctx, const void* qkv, void* out, int n_seq, int S, int heads, int dtype, int q_rows,
                       void* stream);
 
 /* Diagnostics: same as vtq_attention_fwd, and CTA 0 writes clock64() stamps of its pipeline events into

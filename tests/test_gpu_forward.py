@@ -185,3 +185,17 @@ def test_inputs_are_not_mutated_and_training_mode_raises():
     m.train()
     with pytest.raises(RuntimeError, match="inference path only"):
         m((p, p), (pos, pos), (None, None))
+
+
+def test_last_block_pruning_is_exact():
+    """Evaluating the last block only for the quality-token rows changes no score (same kernels, same row math)."""
+    B, N = 3, 200
+    g = torch.Generator(device="cuda").manual_seed(2)
+    p = (torch.randn(B, N, 3, 16, 16, device="cuda", generator=g), torch.randn(B, N, 3, 16, 16, device="cuda", generator=g))
+    pos = (torch.rand(B, N, 2, device="cuda", generator=g), torch.rand(B, N, 2, device="cuda", generator=g))
+    a = _build({}, {}, prune_last_block=True).cuda()
+    b = _build({}, {}, prune_last_block=False).cuda()
+    with torch.no_grad():
+        qa, _ = a(p, pos, (None, None))
+        qb, _ = b(p, pos, (None, None))
+    assert torch.allclose(qa, qb, atol=2e-5), (qa, qb)

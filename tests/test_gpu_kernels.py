@@ -113,7 +113,7 @@ def test_attention(ctx, dt, n_seq, S, heads):
     g = torch.Generator(device="cuda").manual_seed(S)
     qkv = (torch.randn(n_seq * S, 3 * H, device="cuda", generator=g) * 1.5).to(tdt)
     out = torch.full((n_seq * S, H), float("nan"), device="cuda", dtype=tdt)
-    ctx.call("vtq_attention_fwd", P(qkv), P(out), n_seq, S, heads, code, ST())
+    ctx.call("vtq_attention_fwd", P(qkv), P(out), n_seq, S, heads, code, 0, ST())
     torch.cuda.synchronize()
     want = _attn_ref(qkv, n_seq, S, heads)
     assert torch.isfinite(out.float()).all()
@@ -131,12 +131,32 @@ def test_layernorm(ctx, dt, rows):
     w = torch.randn(768, device="cuda", generator=g)
     b = torch.randn(768, device="cuda", generator=g)
     out = torch.empty(rows, 768, device="cuda", dtype=tdt)
-    ctx.call("vtq_layernorm", P(x), P(w), P(b), 1e-6, rows, 768, P(out), code, ST())
+    ctx.call("vtq_layernorm", P(x), 0, P(w), P(b), 1e-6, rows, 768, P(out), code, ST())
     torch.cuda.synchronize()
     want = torch.nn.functional.layer_norm(x, (768,), w, b, 1e-6)
     # identical up to the final 16-bit rounding
     assert (out.float() - want.to(tdt).float()).abs().max().item() <= (0.04 if dt == "bf16" else 0.005)
     assert (out.float() - want).abs().max().item() < (0.05 if dt == "bf16" else 0.006)
+
+
+def test_layernorm_strided_rows_and_attention_row_limit(ctx):
+    """The two ABI features the last-block pruning uses: strided LayerNorm rows, attention limited to leading rows."""
+    g = torch.Generator(device="cuda").manual_seed(4)
+    S, n_seq, H = 301, 3, 768
+    x = torch.randn(n_seq * S, H, device="cuda", generator=g)
+    w = torch.randn(H, device="cuda", generator=g); b = torch.randn(H, device="cuda", generator=g)
+    out = torch.empty(n_seq, H, device="cuda", dtype=torch.float16)
+    ctx.call("vtq_layernorm", P(x), S * H, P(w), P(b), 1e-6, n_seq, H, P(out), 0, ST())
+    want = torch.nn.functional.layer_norm(x[::S], (H,), w, b, 1e-6)
+    qkv = (torch.randn(n_seq * S, 3 * H, device="cuda", generator=g) * 1.5).half()
+    att = torch.full((n_seq * S, H), 7.0, device="cuda", dtype=torch.float16)
+    ctx.call("vtq_attention_fwd", P(qkv), P(att), n_seq, S, 12, 0, 1, ST())
+    torch.cuda.synchronize()
+    assert (out.float() - want).abs().max().item() < 0.006
+    ref = _attn_ref(qkv, n_seq, S, 12).view(n_seq, S, H)
+    got = att.view(n_seq, S, H)
+    assert (got[:, :256].float() - ref[:, :256]).abs().max().item() < 4e-3    # first 256-row granule computed
+    assert torch.all(got[:, 256:] == 7.0)                                     # rows beyond it untouched
 
 
 def test_cast_rows(ctx):

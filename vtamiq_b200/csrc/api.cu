@@ -106,13 +106,13 @@ extern "C" int vtq_gemm(vtq_ctx* ctx, const void* A, int64_t lda, const void* W,
 }
 
 extern "C" int vtq_attention_fwd(vtq_ctx* ctx, const void* qkv, void* out, int n_seq, int S, int heads, int dtype,
-                                 void* stream) {
+                                 int q_rows, void* stream) {
   if (!ctx) return VTQ_ERR_INVALID;
-  return launch_attention(ctx, qkv, out, n_seq, S, heads, dtype, static_cast<cudaStream_t>(stream));
+  return launch_attention(ctx, qkv, out, n_seq, S, heads, dtype, q_rows, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int vtq_attention_fwd_trace(vtq_ctx* ctx, const void* qkv, void* out, int n_seq, int S, int heads,
                                        int dtype, long long* trace, void* stream) {
   if (!ctx) return VTQ_ERR_INVALID;
-  return launch_attention(ctx, qkv, out, n_seq, S, heads, dtype, static_cast<cudaStream_t>(stream), trace);
+  return launch_attention(ctx, qkv, out, n_seq, S, heads, dtype, 0, static_cast<cudaStream_t>(stream), trace);
 }

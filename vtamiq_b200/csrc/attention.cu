@@ -48,7 +48,7 @@ constexpr uint32_t ATT_TMEM_O = 256;  // + t * 64
 template <int DT>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
     attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, int S,
-                     int heads, int n_seq, long long* __restrict__ trace) {
+                     int heads, int n_seq, int q_rows, long long* __restrict__ trace) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B-swizzle atoms need a 1024 B aligned base
   uint8_t* sQ = smem;                                  // [2 buffers][2 tiles]
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
   const int lane = threadIdx.x & 31;
   const int hidden = heads * ATT_D;
   const int nkv = (S + ATT_BKV - 1) / ATT_BKV;
-  const int nqp = (S + 2 * ATT_BQ - 1) / (2 * ATT_BQ);  // query-tile pairs per (sequence, head)
+  const int nqp = (q_rows + 2 * ATT_BQ - 1) / (2 * ATT_BQ);  // query-tile pairs per (sequence, head)
   const int n_items = nqp * heads * n_seq;               // work item = (seq, head, query pair), pair fastest
 
   if (threadIdx.x == 0) {
@@ -385,9 +385,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
 }
 
 int launch_attention(vtq_ctx* ctx, const void* qkv, void* out, int n_seq, int S, int heads, int dtype,
-                     cudaStream_t st, long long* trace) {
+                     int q_rows, cudaStream_t st, long long* trace) {
   VTQ_CHECK_ARG(ctx, qkv && out, "null pointer");
   VTQ_CHECK_ARG(ctx, n_seq >= 1 && S >= 1 && heads >= 1, "empty problem");
+  VTQ_CHECK_ARG(ctx, q_rows >= 0 && q_rows <= S, "q_rows must be in [0, S]");
+  if (q_rows == 0) q_rows = S;
   VTQ_CHECK_ARG(ctx, dtype == VTQ_F16 || dtype == VTQ_BF16, "dtype must be VTQ_F16 or VTQ_BF16");
   VTQ_CHECK_ARG(ctx, (reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out)) % 16 == 0,
                 "pointers must be 16-byte aligned");
@@ -408,7 +410,7 @@ int launch_attention(vtq_ctx* ctx, const void* qkv, void* out, int n_seq, int S,
     int rc = make_tensor_map(ctx, &tmO, dt16, 3, out, dims, strides, box);
     if (rc) return rc;
   }
-  const long long n_items = static_cast<long long>((S + 2 * ATT_BQ - 1) / (2 * ATT_BQ)) * heads * n_seq;
+  const long long n_items = static_cast<long long>((q_rows + 2 * ATT_BQ - 1) / (2 * ATT_BQ)) * heads * n_seq;
   VTQ_CHECK_ARG(ctx, n_items < (1ll << 30), "too many work items");
   dim3 grid(static_cast<unsigned>(n_items < ctx->num_sms ? n_items : ctx->num_sms));
   static bool configured[2] = {false, false};
@@ -419,7 +421,7 @@ int launch_attention(vtq_ctx* ctx, const void* qkv, void* out, int n_seq, int S,
       if (e != cudaSuccess) return check_cuda(ctx, e, "attention: cudaFuncSetAttribute");
       configured[0] = true;
     }
-    attention_kernel<DT_F16><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tmQKV, tmO, S, heads, n_seq, trace);
+    attention_kernel<DT_F16><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tmQKV, tmO, S, heads, n_seq, q_rows, trace);
   } else {
     if (!configured[1]) {
       cudaError_t e = cudaFuncSetAttribute(attention_kernel<DT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -427,7 +429,7 @@ int launch_attention(vtq_ctx* ctx, const void* qkv, void* out, int n_seq, int S,
       if (e != cudaSuccess) return check_cuda(ctx, e, "attention: cudaFuncSetAttribute");
       configured[1] = true;
     }
-    attention_kernel<DT_BF16><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tmQKV, tmO, S, heads, n_seq, trace);
+    attention_kernel<DT_BF16><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tmQKV, tmO, S, heads, n_seq, q_rows, trace);
   }
   VTQ_CHECK_LAUNCH(ctx, "attention launch");
   return VTQ_OK;

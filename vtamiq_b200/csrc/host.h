@@ -50,6 +50,6 @@ inline CUtensorMapDataType tm_dtype16(int dtype) {
 int launch_gemm(vtq_ctx* ctx, const void* A, int64_t lda, const void* W, const float* bias, int M, int N, int K,
                 int dtype, int epilogue, void* out, int64_t ldo, const float* gamma, cudaStream_t st);
 int launch_attention(vtq_ctx* ctx, const void* qkv, void* out, int n_seq, int S, int heads, int dtype,
-                     cudaStream_t st, long long* trace = nullptr);
+                     int q_rows, cudaStream_t st, long long* trace = nullptr);
 
 }  // namespace vtq

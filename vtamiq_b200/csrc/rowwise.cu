@@ -178,14 +178,14 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 template <int DT, int VPL /* float4 per lane */>
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                        const float* __restrict__ b, float eps, size_t rows,
-                                                        void* __restrict__ out16) {
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, size_t x_stride,
+                                                        const float* __restrict__ w, const float* __restrict__ b,
+                                                        float eps, size_t rows, void* __restrict__ out16) {
   constexpr int HIDDEN = VPL * 128;
   const size_t row = blockIdx.x * static_cast<size_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
-  const float4* src = reinterpret_cast<const float4*>(x + row * HIDDEN);
+  const float4* src = reinterpret_cast<const float4*>(x + row * x_stride);
   float4 v[VPL];
   float s = 0.f;
 #pragma unroll
@@ -359,23 +359,26 @@ extern "C" int vtq_embed_assemble(vtq_ctx* ctx, const float* proj, const float* 
   return VTQ_OK;
 }
 
-extern "C" int vtq_layernorm(vtq_ctx* ctx, const float* x, const float* weight, const float* bias, float eps,
-                             int64_t rows, int hidden, void* out16, int dtype, void* stream) {
+extern "C" int vtq_layernorm(vtq_ctx* ctx, const float* x, int64_t x_stride, const float* weight, const float* bias,
+                             float eps, int64_t rows, int hidden, void* out16, int dtype, void* stream) {
   if (!ctx) return VTQ_ERR_INVALID;
   VTQ_CHECK_ARG(ctx, x && weight && bias && out16, "null pointer");
   VTQ_CHECK_ARG(ctx, hidden == 768 || hidden == 1024, "hidden must be 768 or 1024");
   VTQ_CHECK_ARG(ctx, rows >= 0, "rows");
   VTQ_CHECK_ARG(ctx, dtype == VTQ_F16 || dtype == VTQ_BF16, "dtype");
+  if (x_stride <= 0) x_stride = hidden;
+  VTQ_CHECK_ARG(ctx, x_stride >= hidden && x_stride % 4 == 0, "x_stride must be >= hidden and a multiple of 4");
   if (rows == 0) return VTQ_OK;
   const unsigned blocks = static_cast<unsigned>((rows + 7) / 8);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t r = static_cast<size_t>(rows);
+  const size_t xs = static_cast<size_t>(x_stride);
   if (hidden == 768) {
-    if (dtype == VTQ_F16) layernorm_kernel<DT_F16, 6><<<blocks, 256, 0, st>>>(x, weight, bias, eps, r, out16);
-    else layernorm_kernel<DT_BF16, 6><<<blocks, 256, 0, st>>>(x, weight, bias, eps, r, out16);
+    if (dtype == VTQ_F16) layernorm_kernel<DT_F16, 6><<<blocks, 256, 0, st>>>(x, xs, weight, bias, eps, r, out16);
+    else layernorm_kernel<DT_BF16, 6><<<blocks, 256, 0, st>>>(x, xs, weight, bias, eps, r, out16);
   } else {
-    if (dtype == VTQ_F16) layernorm_kernel<DT_F16, 8><<<blocks, 256, 0, st>>>(x, weight, bias, eps, r, out16);
-    else layernorm_kernel<DT_BF16, 8><<<blocks, 256, 0, st>>>(x, weight, bias, eps, r, out16);
+    if (dtype == VTQ_F16) layernorm_kernel<DT_F16, 8><<<blocks, 256, 0, st>>>(x, xs, weight, bias, eps, r, out16);
+    else layernorm_kernel<DT_BF16, 8><<<blocks, 256, 0, st>>>(x, xs, weight, bias, eps, r, out16);
   }
   VTQ_CHECK_LAUNCH(ctx, "layernorm launch");
   return VTQ_OK;

@@ -77,13 +77,15 @@ class _Workspace:
 class Engine:
     """Packed weights + workspaces + launch sequence for one VTAMIQ module on one device."""
 
-    def __init__(self, model, operand_dtype: str = "fp16", use_cuda_graph: bool = True):
+    def __init__(self, model, operand_dtype: str = "fp16", use_cuda_graph: bool = True,
+                 prune_last_block: bool = True):
         if operand_dtype not in _DTYPES:
             raise ValueError(f"operand_dtype must be one of {list(_DTYPES)}")
         self.model = model
         self.operand_dtype = operand_dtype
         self.vtq16, self.torch16 = _DTYPES[operand_dtype]
         self.use_cuda_graph = use_cuda_graph
+        self.prune_last_block = prune_last_block   # last block: quality-token row only after K/V (exact)
         self.device = None
         self.ctx = None
         self._sig = None
@@ -238,14 +240,33 @@ class Engine:
           _ptr(self.extra), self.n_extra, n_seq, N, H, _ptr(ws.x),
           _ptr(ws.pos_idx) if self.dump_indices else None, _ptr(ws.scale_idx) if self.dump_indices else None, st)
         eps = self.ln_eps
-        for L in self.layers:
-            c("layernorm", "vtq_layernorm", _ptr(ws.x), _ptr(L.ln1_w), _ptr(L.ln1_b), eps, rows, H, _ptr(ws.ln), dt, st)
+        n_layers = len(self.layers)
+        for li, L in enumerate(self.layers):
+            c("layernorm", "vtq_layernorm", _ptr(ws.x), 0, _ptr(L.ln1_w), _ptr(L.ln1_b), eps, rows, H, _ptr(ws.ln), dt, st)
             c("gemm_qkv", "vtq_gemm", _ptr(ws.ln), 0, _ptr(L.w_qkv), _ptr(L.b_qkv), rows, 3 * H, H, dt, EPI_BIAS_H,
               _ptr(ws.qkv), 0, None, st)
-            c("attention", "vtq_attention_fwd", _ptr(ws.qkv), _ptr(ws.att), n_seq, S, self.heads, dt, st)
+            if self.prune_last_block and li == n_layers - 1:
+                # Only the quality token of each sequence survives the encoder (transformer.py:634, vtamiq.py:104-108):
+                # in the last block K/V still need every row, but attention output, out-projection, LayerNorm and the
+                # MLP are evaluated for that one row per sequence (row stride S*H picks it out of x / att).
+                tok = self.token_num
+                c("attention_tok", "vtq_attention_fwd", _ptr(ws.qkv), _ptr(ws.att), n_seq, S, self.heads, dt,
+                  tok + 1, st)
+                x_tok = C.c_void_p(ws.x.data_ptr() + tok * H * 4)
+                att_tok = C.c_void_p(ws.att.data_ptr() + tok * H * 2)
+                c("gemm_out_tok", "vtq_gemm", att_tok, S * H, _ptr(L.w_o), _ptr(L.b_o), n_seq, H, H, dt,
+                  EPI_BIAS_RESID_F32, x_tok, S * H, _ptr(L.g1), st)
+                c("layernorm_tok", "vtq_layernorm", x_tok, S * H, _ptr(L.ln2_w), _ptr(L.ln2_b), eps, n_seq, H,
+                  _ptr(ws.ln), dt, st)
+                c("gemm_fc1_tok", "vtq_gemm", _ptr(ws.ln), 0, _ptr(L.w_fc1), _ptr(L.b_fc1), n_seq, self.mlp_dim, H, dt,
+                  EPI_BIAS_GELU_H, _ptr(ws.h1), 0, None, st)
+                c("gemm_fc2_tok", "vtq_gemm", _ptr(ws.h1), 0, _ptr(L.w_fc2), _ptr(L.b_fc2), n_seq, H, self.mlp_dim, dt,
+                  EPI_BIAS_RESID_F32, x_tok, S * H, _ptr(L.g2), st)
+                continue
+            c("attention", "vtq_attention_fwd", _ptr(ws.qkv), _ptr(ws.att), n_seq, S, self.heads, dt, 0, st)
             c("gemm_out", "vtq_gemm", _ptr(ws.att), 0, _ptr(L.w_o), _ptr(L.b_o), rows, H, H, dt, EPI_BIAS_RESID_F32,
               _ptr(ws.x), 0, _ptr(L.g1), st)
-            c("layernorm", "vtq_layernorm", _ptr(ws.x), _ptr(L.ln2_w), _ptr(L.ln2_b), eps, rows, H, _ptr(ws.ln), dt, st)
+            c("layernorm", "vtq_layernorm", _ptr(ws.x), 0, _ptr(L.ln2_w), _ptr(L.ln2_b), eps, rows, H, _ptr(ws.ln), dt, st)
             c("gemm_fc1", "vtq_gemm", _ptr(ws.ln), 0, _ptr(L.w_fc1), _ptr(L.b_fc1), rows, self.mlp_dim, H, dt,
               EPI_BIAS_GELU_H, _ptr(ws.h1), 0, None, st)
             c("gemm_fc2", "vtq_gemm", _ptr(ws.h1), 0, _ptr(L.w_fc2), _ptr(L.b_fc2), rows, H, self.mlp_dim, dt,
@@ -264,7 +285,7 @@ class Engine:
         if not self.use_cuda_graph or self.dump_indices or self.timeline is not None:
             self._encode_and_score(ws, embedded)
             return
-        key = ("emb" if embedded else "patch")
+        key = ("emb" if embedded else "patch", self.prune_last_block)
         if ws.graph is None or ws.graph[0] != key:
             # warm-up outside capture (cudaFuncSetAttribute, lazy module load), then capture
             self._encode_and_score(ws, embedded)
