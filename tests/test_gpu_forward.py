@@ -199,3 +199,87 @@ def test_last_block_pruning_is_exact():
         qa, _ = a(p, pos, (None, None))
         qb, _ = b(p, pos, (None, None))
     assert torch.allclose(qa, qb, atol=2e-5), (qa, qb)
+
+
+def _pairs(B, H, W, counts, seed):
+    """Synthetic graded pairs + jittered per-scale coordinates: images (2,B,3,H,W) and samples list of (B,2,n_s)."""
+    levels = synth.graded_levels(B)
+    rng = np.random.default_rng(seed)
+    imgs = []
+    per_scale = [[] for _ in counts]
+    for p in range(B):
+        ref, dist = synth.make_pair(p, H, W, float(levels[p]))
+        imgs.append(torch.stack([synth.to_tensor_normalized(ref), synth.to_tensor_normalized(dist)]))
+        for s, n in enumerate(counts):
+            per_scale[s].append(synth.jittered_samples(rng, H >> s, W >> s, n))
+    return torch.stack(imgs, dim=1).contiguous(), [np.stack(x) for x in per_scale]
+
+
+def _oracle_scores(sd, images, samples):
+    B = images.shape[1]
+    P, POS, SC = [], [], []
+    for p in range(B):
+        pp, pos, sc = patch_oracle.extract_patches(images[:, p].numpy(), [s[p] for s in samples])
+        P.append(pp); POS.append(pos); SC.append(sc)
+    P, POS = torch.from_numpy(np.stack(P)), torch.from_numpy(np.stack(POS))
+    SCt = torch.from_numpy(np.stack(SC)).float() if SC[0] is not None else None
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    return vtamiq_oracle.vtamiq_forward(sd, (P[:, 0], P[:, 1]), (POS[:, 0], POS[:, 1]),
+                                        (SCt[:, 0], SCt[:, 1]) if SCt is not None else None).numpy()
+
+
+def test_cfg1_single_pair_256_patches():
+    """BASELINE configs[0]: 1 pair 512x384, 256 single-scale patches."""
+    m = _build({}, {})
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m = m.cuda()
+    images, samples = _pairs(1, 384, 512, (256,), seed=11)
+    with torch.no_grad():
+        q = m.forward_from_images(images.cuda(), [torch.from_numpy(s).cuda() for s in samples]).cpu().numpy()
+    assert np.abs(q - _oracle_scores(sd, images, samples)).max() <= SCORE_TOL
+
+
+def test_cfg3_multiscale_1024_scale_embeddings():
+    """BASELINE configs[2] shape: 1024x1024, 3 scales (380/96/24 patches), scale embeddings; reduced batch."""
+    from vtamiq_b200 import compute_num_patches_per_scale
+    counts = tuple(int(c) for c in compute_num_patches_per_scale(500, 3, 2.0)[::-1])
+    assert counts == (380, 96, 24)
+    m = _build(dict(num_scales=3), {})
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m = m.cuda()
+    images, samples = _pairs(4, 1024, 1024, counts, seed=12)
+    with torch.no_grad():
+        q, (p16, pos, scales) = m.forward_from_images(images.cuda(), [torch.from_numpy(s).cuda() for s in samples],
+                                                      return_inputs=True)
+    # scale ids land in scale order 0,0,..,1,..,2 for every image
+    sc = scales.view(2, 4, 500).cpu().numpy()
+    assert (sc[..., :380] == 0).all() and (sc[..., 380:476] == 1).all() and (sc[..., 476:] == 2).all()
+    assert np.abs(q.cpu().numpy() - _oracle_scores(sd, images, samples)).max() <= SCORE_TOL
+
+
+def test_cfg4_long_sequence_5000_patches():
+    """BASELINE configs[3] shape: 3840x2160, 5000 patches (S = 5001: 40 key tiles per row); reduced batch."""
+    m = _build({}, {})
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m = m.cuda()
+    images, samples = _pairs(1, 2160, 3840, (5000,), seed=13)
+    with torch.no_grad():
+        q = m.forward_from_images(images.cuda(), [torch.from_numpy(s).cuda() for s in samples]).cpu().numpy()
+    err = np.abs(q - _oracle_scores(sd, images, samples)).max()
+    print(f"cfg4 S=5001 max|dq|={err:.2e}")
+    assert err <= SCORE_TOL
+
+
+def test_scores_independent_of_batch_split():
+    """Sharding contract: a pair's score does not depend on which other pairs share its batch."""
+    from vtamiq_b200 import shard_pairs
+    m = _build({}, {}).cuda()
+    images, samples = _pairs(6, 96, 128, (64,), seed=14)
+    smp = torch.from_numpy(samples[0]).cuda()
+    with torch.no_grad():
+        full = m.forward_from_images(images.cuda(), [smp])
+        parts = []
+        for r in range(2):
+            a, b = shard_pairs(6, r, 2)
+            parts.append(m.forward_from_images(images[:, a:b].contiguous().cuda(), [smp[a:b].contiguous()]))
+    assert torch.allclose(full, torch.cat(parts), atol=1e-6)
