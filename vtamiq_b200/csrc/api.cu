@@ -9,6 +9,22 @@ namespace vtq {
 
 static std::string g_create_error;  // error of the last failed vtq_create (no handle exists yet)
 
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("VTQ_PDL");
+    return e != nullptr && e[0] == '1';   // measured slightly slower on this path: opt-in
+  }();
+  return on;
+}
+
+bool l2_hints_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("VTQ_L2_HINTS");
+    return e != nullptr && e[0] == '1';   // measured no effect at cfg2: opt-in
+  }();
+  return on;
+}
+
 int fail(vtq_ctx* ctx, int code, const std::string& msg) {
   if (ctx) ctx->last_error = msg;
   else g_create_error = msg;

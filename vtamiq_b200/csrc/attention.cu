@@ -48,7 +48,7 @@ constexpr uint32_t ATT_TMEM_O = 256;  // + t * 64
 template <int DT>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
     attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, int S,
-                     int heads, int n_seq, int q_rows, long long* __restrict__ trace) {
+                     int heads, int n_seq, int q_rows, uint64_t hint_qkv, long long* __restrict__ trace) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B-swizzle atoms need a 1024 B aligned base
   uint8_t* sQ = smem;                                  // [2 buffers][2 tiles]
@@ -101,6 +101,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -116,14 +118,17 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
           const uint32_t qb = it & 1;
           mbar_wait(&q_empty[qb], ((it >> 1) & 1) ^ 1);
           mbar_expect_tx(&q_full[qb], 2 * ATT_TILE_BYTES);
-          tma_load_3d(sQ + (2 * qb) * ATT_TILE_BYTES, &tmQKV, &q_full[qb], head * ATT_D, q0, seq);
-          tma_load_3d(sQ + (2 * qb + 1) * ATT_TILE_BYTES, &tmQKV, &q_full[qb], head * ATT_D, q0 + ATT_BQ, seq);
+          tma_load_3d_hint(sQ + (2 * qb) * ATT_TILE_BYTES, &tmQKV, &q_full[qb], head * ATT_D, q0, seq, hint_qkv);
+          tma_load_3d_hint(sQ + (2 * qb + 1) * ATT_TILE_BYTES, &tmQKV, &q_full[qb], head * ATT_D, q0 + ATT_BQ, seq,
+                           hint_qkv);
           for (int j = 0; j < nkv; ++j, ++kvc) {
             const uint32_t st = kvc % ATT_KV_STAGES;
             mbar_wait(&kv_empty[st], ((kvc / ATT_KV_STAGES) & 1) ^ 1);
             mbar_expect_tx(&kv_full[st], 2 * ATT_TILE_BYTES);
-            tma_load_3d(sK + st * ATT_TILE_BYTES, &tmQKV, &kv_full[st], hidden + head * ATT_D, j * ATT_BKV, seq);
-            tma_load_3d(sV + st * ATT_TILE_BYTES, &tmQKV, &kv_full[st], 2 * hidden + head * ATT_D, j * ATT_BKV, seq);
+            tma_load_3d_hint(sK + st * ATT_TILE_BYTES, &tmQKV, &kv_full[st], hidden + head * ATT_D, j * ATT_BKV, seq,
+                             hint_qkv);
+            tma_load_3d_hint(sV + st * ATT_TILE_BYTES, &tmQKV, &kv_full[st], 2 * hidden + head * ATT_D, j * ATT_BKV,
+                             seq, hint_qkv);
           }
         }
       }
@@ -413,6 +418,8 @@ int launch_attention(vtq_ctx* ctx, const void* qkv, void* out, int n_seq, int S,
   const long long n_items = static_cast<long long>((q_rows + 2 * ATT_BQ - 1) / (2 * ATT_BQ)) * heads * n_seq;
   VTQ_CHECK_ARG(ctx, n_items < (1ll << 30), "too many work items");
   dim3 grid(static_cast<unsigned>(n_items < ctx->num_sms ? n_items : ctx->num_sms));
+  // q|k|v rows are dead after this kernel: let them leave L2 first (keeps the residual stream resident)
+  const uint64_t hint_qkv = l2_hints_enabled() ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
   static bool configured[2] = {false, false};
   if (dtype == VTQ_F16) {
     if (!configured[0]) {
@@ -421,7 +428,9 @@ int launch_attention(vtq_ctx* ctx, const void* qkv, void* out, int n_seq, int S,
       if (e != cudaSuccess) return check_cuda(ctx, e, "attention: cudaFuncSetAttribute");
       configured[0] = true;
     }
-    attention_kernel<DT_F16><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tmQKV, tmO, S, heads, n_seq, q_rows, trace);
+    cudaError_t le = launch_pdl(attention_kernel<DT_F16>, grid, dim3(ATT_THREADS), ATT_SMEM_BYTES, st, tmQKV, tmO, S,
+                                heads, n_seq, q_rows, hint_qkv, trace);
+    if (le != cudaSuccess) return check_cuda(ctx, le, "attention launch");
   } else {
     if (!configured[1]) {
       cudaError_t e = cudaFuncSetAttribute(attention_kernel<DT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -429,7 +438,9 @@ int launch_attention(vtq_ctx* ctx, const void* qkv, void* out, int n_seq, int S,
       if (e != cudaSuccess) return check_cuda(ctx, e, "attention: cudaFuncSetAttribute");
       configured[1] = true;
     }
-    attention_kernel<DT_BF16><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tmQKV, tmO, S, heads, n_seq, q_rows, trace);
+    cudaError_t le = launch_pdl(attention_kernel<DT_BF16>, grid, dim3(ATT_THREADS), ATT_SMEM_BYTES, st, tmQKV, tmO, S,
+                                heads, n_seq, q_rows, hint_qkv, trace);
+    if (le != cudaSuccess) return check_cuda(ctx, le, "attention launch");
   }
   VTQ_CHECK_LAUNCH(ctx, "attention launch");
   return VTQ_OK;

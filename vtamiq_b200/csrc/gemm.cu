@@ -65,7 +65,8 @@ __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
 template <int DT, int BN, int EPI, bool GELU>
 __device__ __forceinline__ void epilogue_tile(uint32_t t_row, int row0, int n0, int N, const float* __restrict__ bias,
                                               const float* __restrict__ gamma, int accumulate,
-                                              const CUtensorMap* tmO, uint8_t* buf, int lane, int half) {
+                                              const CUtensorMap* tmO, uint8_t* buf, int lane, int half,
+                                              uint64_t hint_o) {
   const uint32_t swz = static_cast<uint32_t>(lane & 7);
   if constexpr (EPI == EPI_F32) {
     // 32 fp32 columns (128 B per row) per staged box
@@ -96,8 +97,8 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_row, int row0, int n0, 
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        if (accumulate) tma_reduce_add_2d(tmO, buf, ncol, row0);
-        else tma_store_2d(tmO, buf, ncol, row0);
+        if (accumulate) tma_reduce_add_2d_hint(tmO, buf, ncol, row0, hint_o);
+        else tma_store_2d_hint(tmO, buf, ncol, row0, hint_o);
         tma_commit_group();
       }
     }
@@ -140,7 +141,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_row, int row0, int n0, 
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        tma_store_2d(tmO, buf, ncol, row0);
+        tma_store_2d_hint(tmO, buf, ncol, row0, hint_o);
         tma_commit_group();
       }
     }
@@ -164,7 +165,8 @@ template <int DT, int BN, int EPI, bool GELU>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmO, const float* __restrict__ bias,
-                const float* __restrict__ gamma, int M, int N, int K, int accumulate) {
+                const float* __restrict__ gamma, int M, int N, int K, int accumulate, uint64_t hint_a,
+                uint64_t hint_o) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B-swizzle atoms need a 1024 B aligned base
@@ -204,6 +206,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_launch_dependents();  // the next kernel may set itself up while this one runs ...
+  pdl_wait();               // ... and this one touches global memory only after its predecessor completed
 
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------
@@ -217,8 +221,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           uint8_t* sa = ring + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + GEMM_A_BYTES;
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m0);
-          tma_load_2d(sb, &tmB, &full_bar[stage], kb * GEMM_BK, n0);
+          tma_load_2d_hint(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m0, hint_a);
+          tma_load_2d_hint(sb, &tmB, &full_bar[stage], kb * GEMM_BK, n0, L2_EVICT_LAST);  // weights: hot
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -269,7 +273,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + acc * Cfg::ACC_STRIDE;
       epilogue_tile<DT, BN, EPI, GELU>(t_row, m0 + lane_grp * 32, n0, N, bias, gamma, accumulate, &tmO, my_staging,
-                                       lane, half);
+                                       lane, half, hint_o);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);  // one arrival per epilogue warp
@@ -295,10 +299,12 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // TMA load whose completion bytes are credited to the LEADER CTA's mbarrier (peer bit cleared)
-__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                 uint64_t hint) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1),
+      "l"(hint)
       : "memory");
 }
 __device__ __forceinline__ void umma_f16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
@@ -359,7 +365,8 @@ template <int DT, int BN, int EPI, bool GELU>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const float* __restrict__ bias,
-                 const float* __restrict__ gamma, int M, int N, int K, int accumulate) {
+                 const float* __restrict__ gamma, int M, int N, int K, int accumulate, uint64_t hint_a,
+                 uint64_t hint_o) {
   using Cfg = Gemm2Cfg<BN>;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -403,6 +410,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
   cluster_sync_all();  // barrier inits + TMEM allocation visible in both CTAs before any remote arrival
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------- TMA producer (both CTAs) -------------------
@@ -416,8 +425,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
           uint8_t* sa = ring + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + GEMM_A_BYTES;
           if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);  // both CTAs' bytes land here
-          tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m0);
-          tma_load_2d_pair(sb, &tmB, &full_bar[stage], kb * GEMM_BK, n0);
+          tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m0, hint_a);
+          tma_load_2d_pair(sb, &tmB, &full_bar[stage], kb * GEMM_BK, n0, L2_EVICT_LAST);  // weights: hot
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -466,7 +475,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + acc * Cfg::ACC_STRIDE;
       epilogue_tile<DT, BN, EPI, GELU>(t_row, m0 + lane_grp * 32, n0, N, bias, gamma, accumulate, &tmO, my_staging,
-                                       lane, half);
+                                       lane, half, hint_o);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&acc_empty[acc], 0);  // one arrival per epilogue warp, on the leader
@@ -485,7 +494,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 template <int DT, int BN, int EPI, bool GELU>
 static int launch_1cta(vtq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
                        const float* bias, const float* gamma, int M, int N, int K, int accumulate,
-                       cudaStream_t st) {
+                       uint64_t hint_a, uint64_t hint_o, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_kernel<DT, BN, EPI, GELU>;
   static bool configured = false;  // per instantiation
@@ -496,7 +505,9 @@ static int launch_1cta(vtq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& 
   }
   const int num_tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
   const int grid = num_tiles < ctx->num_sms ? num_tiles : ctx->num_sms;
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmO, bias, gamma, M, N, K, accumulate);
+  cudaError_t le = launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, st, tmA, tmB, tmO, bias, gamma, M,
+                              N, K, accumulate, hint_a, hint_o);
+  if (le != cudaSuccess) return check_cuda(ctx, le, "gemm launch");
   VTQ_CHECK_LAUNCH(ctx, "gemm launch");
   return VTQ_OK;
 }
@@ -504,7 +515,7 @@ static int launch_1cta(vtq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& 
 template <int DT, int BN, int EPI, bool GELU>
 static int launch_2cta(vtq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
                        const float* bias, const float* gamma, int M, int N, int K, int accumulate,
-                       cudaStream_t st) {
+                       uint64_t hint_a, uint64_t hint_o, cudaStream_t st) {
   using Cfg = Gemm2Cfg<BN>;
   auto kern = gemm2_kernel<DT, BN, EPI, GELU>;
   static bool configured = false;
@@ -516,7 +527,9 @@ static int launch_2cta(vtq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& 
   const int num_tiles = ((M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * ((N + BN - 1) / BN);
   const int max_pairs = ctx->num_sms / 2;
   const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;
-  kern<<<2 * pairs, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmO, bias, gamma, M, N, K, accumulate);
+  cudaError_t le = launch_pdl(kern, dim3(2 * pairs), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, st, tmA, tmB, tmO, bias,
+                              gamma, M, N, K, accumulate, hint_a, hint_o);
+  if (le != cudaSuccess) return check_cuda(ctx, le, "gemm2 launch");
   VTQ_CHECK_LAUNCH(ctx, "gemm2 launch");
   return VTQ_OK;
 }
@@ -575,12 +588,21 @@ int launch_gemm(vtq_ctx* ctx, const void* A, int64_t lda, const void* W, const f
   }
   const int acc = epilogue == VTQ_EPI_BIAS_RESID_F32 ? 1 : 0;
   if (epilogue != VTQ_EPI_BIAS_RESID_F32) gamma = nullptr;
+  // L2 residency plan: the fp32 residual stream x (98 MB at cfg2) is the one buffer every block
+  // re-reads, so the residual GEMMs pin it (reduce-add with evict_last) and mark their dead-after-use A operand
+  // (attention output / fc1 activations) evict_first; the wide 16-bit outputs (qkv, h1) are written evict_first
+  // so they stream through L2 instead of flushing x and the normalised activations.
+  uint64_t hint_a = L2_EVICT_NORMAL, hint_o = L2_EVICT_NORMAL;
+  if (l2_hints_enabled()) {
+    if (epilogue == VTQ_EPI_BIAS_RESID_F32) { hint_a = L2_EVICT_FIRST; hint_o = L2_EVICT_LAST; }
+    else if (epilogue != VTQ_EPI_BIAS_F32) { hint_o = L2_EVICT_FIRST; }
+  }
 
 #define VTQ_GEMM_EPI(FN, DTV, BNV)                                                                          \
   switch (epilogue) {                                                                                       \
-    case VTQ_EPI_BIAS_H: return FN<DTV, BNV, EPI_H, false>(ctx, tmA, tmB, tmO, bias, gamma, M, N, K, 0, st); \
-    case VTQ_EPI_BIAS_GELU_H: return FN<DTV, BNV, EPI_H, true>(ctx, tmA, tmB, tmO, bias, gamma, M, N, K, 0, st); \
-    default: return FN<DTV, BNV, EPI_F32, false>(ctx, tmA, tmB, tmO, bias, gamma, M, N, K, acc, st);        \
+    case VTQ_EPI_BIAS_H: return FN<DTV, BNV, EPI_H, false>(ctx, tmA, tmB, tmO, bias, gamma, M, N, K, 0, hint_a, hint_o, st); \
+    case VTQ_EPI_BIAS_GELU_H: return FN<DTV, BNV, EPI_H, true>(ctx, tmA, tmB, tmO, bias, gamma, M, N, K, 0, hint_a, hint_o, st); \
+    default: return FN<DTV, BNV, EPI_F32, false>(ctx, tmA, tmB, tmO, bias, gamma, M, N, K, acc, hint_a, hint_o, st);        \
   }
 #define VTQ_GEMM_DT(FN, BNV)                                     \
   if (dtype == VTQ_F16) { VTQ_GEMM_EPI(FN, DT_F16, BNV) } else { VTQ_GEMM_EPI(FN, DT_BF16, BNV) }

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
 #include <string>
 
 #include "../../include/vtamiq_b200.h"
@@ -45,6 +46,27 @@ inline CUtensorMapDataType tm_dtype16(int dtype) {
     cudaError_t e__ = cudaGetLastError();                                  \
     if (e__ != cudaSuccess) return ::vtq::check_cuda((ctx), e__, (what));  \
   } while (0)
+
+// Launch with Programmatic Dependent Launch enabled: the kernel may become resident while its predecessor in the
+// stream drains, run its setup (barrier init, TMEM allocation, descriptor prefetch) and then blocks in
+// griddepcontrol.wait until the predecessor has completed and its writes are visible.  Opt-in: VTQ_PDL=1.
+bool pdl_enabled();
+bool l2_hints_enabled();  // VTQ_L2_HINTS=1 turns the L2 eviction-priority hints on (A/B switch, default off)
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // per-kernel launchers (defined next to their kernels)
 int launch_gemm(vtq_ctx* ctx, const void* A, int64_t lda, const void* W, const float* bias, int M, int N, int K,

@@ -177,11 +177,22 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+__device__ __forceinline__ float4 ld_f4_hint(const float4* p, uint64_t hint) {
+  float4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(hint));
+  return v;
+}
+
 template <int DT, int VPL /* float4 per lane */>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, size_t x_stride,
                                                         const float* __restrict__ w, const float* __restrict__ b,
-                                                        float eps, size_t rows, void* __restrict__ out16) {
+                                                        float eps, size_t rows, void* __restrict__ out16,
+                                                        uint64_t hint_x) {
   constexpr int HIDDEN = VPL * 128;
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t row = blockIdx.x * static_cast<size_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -189,10 +200,9 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   float4 v[VPL];
   float s = 0.f;
 #pragma unroll
-  for (int k = 0; k < VPL; ++k) {
-    v[k] = src[lane + 32 * k];
-    s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
-  }
+  for (int k = 0; k < VPL; ++k) v[k] = ld_f4_hint(src + lane + 32 * k, hint_x);  // keep x resident in L2
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
   const float mean = warp_sum(s) * (1.0f / HIDDEN);
   float q = 0.f;
 #pragma unroll
@@ -373,13 +383,16 @@ extern "C" int vtq_layernorm(vtq_ctx* ctx, const float* x, int64_t x_stride, con
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t r = static_cast<size_t>(rows);
   const size_t xs = static_cast<size_t>(x_stride);
+  const uint64_t hint_x = l2_hints_enabled() ? L2_EVICT_LAST : L2_EVICT_NORMAL;
+  cudaError_t le;
   if (hidden == 768) {
-    if (dtype == VTQ_F16) layernorm_kernel<DT_F16, 6><<<blocks, 256, 0, st>>>(x, xs, weight, bias, eps, r, out16);
-    else layernorm_kernel<DT_BF16, 6><<<blocks, 256, 0, st>>>(x, xs, weight, bias, eps, r, out16);
+    if (dtype == VTQ_F16) le = launch_pdl(layernorm_kernel<DT_F16, 6>, dim3(blocks), dim3(256), 0, st, x, xs, weight, bias, eps, r, out16, hint_x);
+    else le = launch_pdl(layernorm_kernel<DT_BF16, 6>, dim3(blocks), dim3(256), 0, st, x, xs, weight, bias, eps, r, out16, hint_x);
   } else {
-    if (dtype == VTQ_F16) layernorm_kernel<DT_F16, 8><<<blocks, 256, 0, st>>>(x, xs, weight, bias, eps, r, out16);
-    else layernorm_kernel<DT_BF16, 8><<<blocks, 256, 0, st>>>(x, xs, weight, bias, eps, r, out16);
+    if (dtype == VTQ_F16) le = launch_pdl(layernorm_kernel<DT_F16, 8>, dim3(blocks), dim3(256), 0, st, x, xs, weight, bias, eps, r, out16, hint_x);
+    else le = launch_pdl(layernorm_kernel<DT_BF16, 8>, dim3(blocks), dim3(256), 0, st, x, xs, weight, bias, eps, r, out16, hint_x);
   }
+  if (le != cudaSuccess) return check_cuda(ctx, le, "layernorm launch");
   VTQ_CHECK_LAUNCH(ctx, "layernorm launch");
   return VTQ_OK;
 }
