@@ -74,6 +74,17 @@ int vtq_patch_gather(vtq_ctx* ctx, const float* images, int n_img, int H, int W,
                      int n, int patch_offset, int N_total, float* patches_f32, void* patches_16, int dtype,
                      float* pos, float* scales, int scale_id, void* stream);
 
+/* K1 with the image transform fused in (SURVEY §8f "next" #2).  images [n_img][H][W][3] uint8 (as decoded); each
+ * pixel goes through the reference's transform_img arithmetic — x/255, then (x-0.5)/0.5, fp32, in that order
+ * (data/utils.py:76,:94; data/patch_datasets.py:51-52) — inside the gather, so outputs are bit-identical to gathering
+ * from the transformed fp32 tensor.  Single level (all n patches of N_total = n). */
+int vtq_patch_gather_u8(vtq_ctx* ctx, const uint8_t* images, int n_img, int H, int W, const double* samples, int n_set,
+                        int n, float* patches_f32, void* patches_16, int dtype, float* pos, void* stream);
+
+/* The same transform for whole images: uint8 [n_img][H][W][3] -> fp32 [n_img][3][H][W]; only needed in front of the
+ * pyramid when more than one scale is sampled. */
+int vtq_normalize_u8(vtq_ctx* ctx, const uint8_t* src, float* dst, int n_img, int H, int W, void* stream);
+
 /* 2x2 mean pyramid level, floor mode, summation order ((a00+a01)+a10)+a11 then *0.25
  * replaces nn.AvgPool2d(2) at data/patch_sampling.py:552,:600.  src [planes][H][W] -> dst [planes][H/2][W/2] */
 int vtq_avgpool2x2(vtq_ctx* ctx, const float* src, float* dst, int planes, int H, int W, void* stream);

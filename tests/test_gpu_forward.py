@@ -283,3 +283,17 @@ def test_scores_independent_of_batch_split():
             a, b = shard_pairs(6, r, 2)
             parts.append(m.forward_from_images(images[:, a:b].contiguous().cuda(), [smp[a:b].contiguous()]))
     assert torch.allclose(full, torch.cat(parts), atol=1e-6)
+
+
+def test_forward_from_uint8_images_matches_fp32_images():
+    """The fused uint8 -> normalise -> gather entry gives the same scores as feeding the transformed fp32 images."""
+    m = _build({}, {}).cuda()
+    B, H, W, N = 3, 96, 128, 64
+    rng = np.random.default_rng(21)
+    u8 = np.stack([np.stack([synth.make_pair(p, H, W, 0.1)[k] for p in range(B)]) for k in range(2)])   # (2,B,H,W,3)
+    f32 = torch.stack([torch.stack([synth.to_tensor_normalized(u8[k, p]) for p in range(B)]) for k in range(2)])
+    smp = [torch.from_numpy(np.stack([synth.jittered_samples(rng, H, W, N) for _ in range(B)])).cuda()]
+    with torch.no_grad():
+        qa = m.forward_from_images(torch.from_numpy(u8).cuda(), smp)
+        qb = m.forward_from_images(f32.cuda(), smp)
+    assert torch.equal(qa, qb)

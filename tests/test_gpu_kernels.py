@@ -284,3 +284,18 @@ def test_avgpool_bit_exact(ctx):
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy().view(np.uint32), patch_oracle.avgpool2x2(x.cpu().numpy()).view(np.uint32))
     assert np.array_equal(out2.cpu().numpy().view(np.uint32), patch_oracle.avgpool2x2(y.cpu().numpy()).view(np.uint32))
+
+
+@pytest.mark.parametrize("case", ["single", "multi3", "odd2"])
+def test_patch_gather_from_uint8_bit_exact(golden_dir, case):
+    """uint8 HWC source with the reference transform fused in (or applied on device in front of the pyramid)."""
+    from vtamiq_b200 import extract_patches
+    g = np.load(os.path.join(golden_dir, f"patches_{case}.npz"))
+    u8 = torch.from_numpy(np.stack([g["ref_u8"], g["dist_u8"]])).cuda()      # (2, H, W, 3) uint8
+    smp = [g[f"samples_{i}"] for i in range(int(g["n_levels"]))]
+    patches, pos, scales = extract_patches(u8, smp)
+    torch.cuda.synchronize()
+    assert np.array_equal(patches.cpu().numpy().view(np.uint32), g["patches"].view(np.uint32))
+    assert np.array_equal(pos.cpu().numpy().view(np.uint32), g["pos"].view(np.uint32))
+    if "scales" in g.files:
+        assert np.array_equal(scales.cpu().numpy(), g["scales"])

@@ -27,6 +27,8 @@ SIGNATURES = {
     "vtq_launch_count": (C.c_ulonglong, [_vp]),
     "vtq_workspace_bytes": (_i64, [_vp, _i, _i]),
     "vtq_patch_gather": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp]),
+    "vtq_patch_gather_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "vtq_normalize_u8": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "vtq_avgpool2x2": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "vtq_cast_rows": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
     "vtq_embed_assemble": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),

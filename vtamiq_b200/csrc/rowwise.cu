@@ -59,6 +59,63 @@ __global__ void __launch_bounds__(192) patch_gather_kernel(const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
+// K1 (uint8 source): the reference decodes to uint8 HWC, then to_tensor (/255) and normalize ((x-.5)/.5)
+// (data/utils.py:76,:94; patch_datasets.py:51-52) before gathering.  Fusing that transform into the gather keeps
+// the images in HBM as uint8 (4x fewer bytes) and never materialises the fp32 image; the three fp32 operations
+// are performed in the reference's order with IEEE-rounded intrinsics, so the patches are bit-identical.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float normalize_u8(uint8_t u) {
+  return __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(u), 255.0f), 0.5f), 0.5f);
+}
+
+template <int DT>
+__global__ void __launch_bounds__(192) patch_gather_u8_kernel(const uint8_t* __restrict__ images, int H, int W,
+                                                              const double* __restrict__ samples, int n_set, int n,
+                                                              int N_total, float* __restrict__ patches_f32,
+                                                              void* __restrict__ patches_16, float* __restrict__ pos) {
+  const int p = blockIdx.x;
+  const int img = blockIdx.y;
+  const int set = img % n_set;
+  const double sy = samples[(static_cast<size_t>(set) * 2 + 0) * n + p];
+  const double sx = samples[(static_cast<size_t>(set) * 2 + 1) * n + p];
+  const int y0 = static_cast<int>(sy);
+  const int x0 = static_cast<int>(sx);
+  const size_t slot = static_cast<size_t>(img) * N_total + p;
+  const int t = threadIdx.x;    // (c, i, j4)
+  const int c = t >> 6;
+  const int i = (t >> 2) & 15;
+  const int j4 = (t & 3) * 4;
+  const uint8_t* src = images + ((static_cast<size_t>(img) * H + (y0 + i)) * W + x0 + j4) * 3 + c;  // HWC
+  const float v0 = normalize_u8(__ldg(src)), v1 = normalize_u8(__ldg(src + 3)), v2 = normalize_u8(__ldg(src + 6)),
+              v3 = normalize_u8(__ldg(src + 9));
+  const size_t o = slot * PATCH_ELEMS + static_cast<size_t>(t) * 4;
+  if (patches_f32 != nullptr) *reinterpret_cast<float4*>(patches_f32 + o) = make_float4(v0, v1, v2, v3);
+  if (patches_16 != nullptr)
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(patches_16) + o) = make_uint2(pack2<DT>(v0, v1), pack2<DT>(v2, v3));
+  if (t == 0 && pos != nullptr) {
+    const double hi = 1.0 - 1e-6;
+    double u = (sy + 8.0) / static_cast<double>(static_cast<float>(H - 8));
+    double v = (sx + 8.0) / static_cast<double>(static_cast<float>(W - 8));
+    pos[slot * 2 + 0] = __double2float_rn(fmin(fmax(u, 0.0), hi));
+    pos[slot * 2 + 1] = __double2float_rn(fmin(fmax(v, 0.0), hi));
+  }
+}
+
+// uint8 HWC -> normalised fp32 CHW (needed only in front of the pyramid for multi-scale sampling)
+__global__ void normalize_u8_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, int H, int W,
+                                    size_t total) {
+  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;  // over [img][c][y][x]
+  if (idx >= total) return;
+  const int x = static_cast<int>(idx % W);
+  size_t rem = idx / W;
+  const int y = static_cast<int>(rem % H);
+  rem /= H;
+  const int c = static_cast<int>(rem % 3);
+  const size_t img = rem / 3;
+  dst[idx] = normalize_u8(__ldg(src + ((img * H + y) * W + x) * 3 + c));
+}
+
+// ------------------------------------------------------------------------------------------------
 // 2x2 mean, floor mode; the summation tree and the exact /4 follow ATen's avg_pool2d (kh outer, kw inner).
 // ------------------------------------------------------------------------------------------------
 __global__ void avgpool2x2_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int W, int Ho,
@@ -409,5 +466,36 @@ extern "C" int vtq_cls_diff(vtq_ctx* ctx, const float* x, int B, int S, int hidd
   if (hidden == 768) cls_diff_kernel<6><<<blocks, 128, 0, st>>>(x, B, S, token, ln_weight, ln_bias, eps, gamma, diff);
   else cls_diff_kernel<8><<<blocks, 128, 0, st>>>(x, B, S, token, ln_weight, ln_bias, eps, gamma, diff);
   VTQ_CHECK_LAUNCH(ctx, "cls_diff launch");
+  return VTQ_OK;
+}
+
+extern "C" int vtq_patch_gather_u8(vtq_ctx* ctx, const uint8_t* images, int n_img, int H, int W,
+                                   const double* samples, int n_set, int n, float* patches_f32, void* patches_16,
+                                   int dtype, float* pos, void* stream) {
+  if (!ctx) return VTQ_ERR_INVALID;
+  VTQ_CHECK_ARG(ctx, images && samples, "null pointer");
+  VTQ_CHECK_ARG(ctx, H >= PATCH && W >= PATCH, "image smaller than one patch");
+  VTQ_CHECK_ARG(ctx, n_img >= 1 && n_set >= 1 && n_img % n_set == 0, "n_img must be a multiple of n_set");
+  VTQ_CHECK_ARG(ctx, n >= 0 && n_img <= 65535, "patch / image count");
+  VTQ_CHECK_ARG(ctx, dtype == VTQ_F16 || dtype == VTQ_BF16, "dtype");
+  if (n == 0) return VTQ_OK;
+  dim3 grid(n, n_img);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == VTQ_F16)
+    patch_gather_u8_kernel<DT_F16><<<grid, 192, 0, st>>>(images, H, W, samples, n_set, n, n, patches_f32, patches_16, pos);
+  else
+    patch_gather_u8_kernel<DT_BF16><<<grid, 192, 0, st>>>(images, H, W, samples, n_set, n, n, patches_f32, patches_16, pos);
+  VTQ_CHECK_LAUNCH(ctx, "patch_gather_u8 launch");
+  return VTQ_OK;
+}
+
+extern "C" int vtq_normalize_u8(vtq_ctx* ctx, const uint8_t* src, float* dst, int n_img, int H, int W, void* stream) {
+  if (!ctx) return VTQ_ERR_INVALID;
+  VTQ_CHECK_ARG(ctx, src && dst, "null pointer");
+  VTQ_CHECK_ARG(ctx, n_img >= 1 && H >= 1 && W >= 1, "shape");
+  const size_t total = static_cast<size_t>(n_img) * 3 * H * W;
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  normalize_u8_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, H, W, total);
+  VTQ_CHECK_LAUNCH(ctx, "normalize_u8 launch");
   return VTQ_OK;
 }

@@ -57,8 +57,32 @@ def _pyramid(ctx, level0: torch.Tensor, num_levels: int):
     return levels
 
 
+def _normalize_u8(ctx, images_u8: torch.Tensor) -> torch.Tensor:
+    """uint8 (..., H, W, 3) -> normalised fp32 (..., 3, H, W) with the reference's transform arithmetic."""
+    lead, (H, W) = images_u8.shape[:-3], images_u8.shape[-3:-1]
+    out = torch.empty(*lead, 3, H, W, dtype=torch.float32, device=images_u8.device)
+    ctx.call("vtq_normalize_u8", _ptr(images_u8), _ptr(out), images_u8.numel() // (3 * H * W), H, W, _stream())
+    return out
+
+
 def gather_into_workspace(eng, ws, images: torch.Tensor, samples):
-    """Fill ws.patches16 / ws.pos / ws.scales for ``Engine.run`` from (2,B,3,H,W) images + per-scale coords."""
+    """Fill ws.patches16 / ws.pos / ws.scales for ``Engine.run`` from images + per-scale coordinates.
+    images: (2,B,3,H,W) fp32 normalised, or (2,B,H,W,3) uint8 as decoded (transform fused into the gather)."""
+    if images.dtype == torch.uint8:
+        if images.dim() != 5 or images.shape[0] != 2 or images.shape[4] != 3:
+            raise ValueError("uint8 images must be (2, B, H, W, 3)")
+        images = images.contiguous()
+        B, H, W = images.shape[1], images.shape[2], images.shape[3]
+        if len(samples) == 1:
+            smp = samples[0]
+            if smp.dtype != torch.float64 or smp.shape[0] != B or smp.shape[1] != 2 or smp.shape[2] != ws.N:
+                raise ValueError("samples[0] must be float64 (B, 2, N)")
+            eng.ctx.call("vtq_patch_gather_u8", _ptr(images), 2 * B, H, W, _ptr(smp.contiguous()), B, ws.N, None,
+                         _ptr(ws.patches16), eng.vtq16, _ptr(ws.pos), _stream())
+            if eng.scale_table is not None:
+                ws.scales.zero_()
+            return
+        images = _normalize_u8(eng.ctx, images)   # multi-scale: the pyramid is built from the fp32 image
     if images.dim() != 5 or images.shape[0] != 2 or images.shape[2] != 3:
         raise ValueError("images must be (2, B, 3, H, W)")
     if images.dtype != torch.float32 or not images.is_contiguous():
@@ -94,6 +118,19 @@ def extract_patches(tensors: torch.Tensor, samples, patch_dim: int = 16, with_sc
     if tensors.device.type != "cuda":
         raise RuntimeError("extract_patches runs on the GPU only (no CPU path)")
     ctx = get_context(tensors.device.index if tensors.device.index is not None else torch.cuda.current_device())
+    if tensors.dtype == torch.uint8:      # (K, H, W, 3) as decoded: fuse / apply the reference transform on device
+        tensors = tensors.contiguous()
+        if len(samples) == 1:
+            K, H, W = tensors.shape[0], tensors.shape[1], tensors.shape[2]
+            sm = torch.as_tensor(np.asarray(samples[0]), dtype=torch.float64).to(tensors.device).reshape(1, 2, -1).contiguous()
+            N = sm.shape[-1]
+            patches = torch.zeros(K, N, 3, patch_dim, patch_dim, dtype=torch.float32, device=tensors.device)
+            pos = torch.zeros(K, N, 2, dtype=torch.float32, device=tensors.device)
+            ctx.call("vtq_patch_gather_u8", _ptr(tensors), K, H, W, _ptr(sm), 1, N, _ptr(patches), None, VTQ_F16,
+                     _ptr(pos), _stream())
+            sc = torch.zeros(K, N, dtype=torch.int32, device=tensors.device) if with_scales else None
+            return patches, pos, sc
+        tensors = _normalize_u8(ctx, tensors)
     if tensors.dtype != torch.float32 or not tensors.is_contiguous():
         tensors = tensors.to(torch.float32).contiguous()
     K = tensors.shape[0]

@@ -134,7 +134,9 @@ class VTAMIQ(VisionTransformerBackbone):
     def forward_from_images(self, images, samples, return_inputs=False):
         """Device-side patch extraction fused in front of the forward.
 
-        images  : (2, B, 3, H, W) fp32 on the model's device, already normalised ((x-.5)/.5), [0] = ref block.
+        images  : (2, B, 3, H, W) fp32 on the model's device, already normalised ((x-.5)/.5), [0] = ref block;
+                  or (2, B, H, W, 3) uint8 as decoded — the reference's to_tensor + normalize arithmetic is then
+                  applied on the device (fused into the gather when a single scale is sampled), bit-identically.
         samples : list over scales s=0.. of float64 (B, 2, n_s) top-left coordinates in the level-s image
                   (row 0 = y), as ``PatchSampler.get_sample_params`` returns them; ref and dist share them.
         Returns q (B,), or (q, (patches16, pos, scales)) views of the staged inputs when return_inputs.
@@ -145,6 +147,8 @@ class VTAMIQ(VisionTransformerBackbone):
         with torch.no_grad():
             B = images.shape[1]
             N = int(sum(s.shape[-1] for s in samples))
+            if images.device != next(self.parameters()).device:
+                raise ValueError("images must live on the model's device")
             ws = eng.workspace(B, N)
             gather_into_workspace(eng, ws, images, samples)
             eng.run(ws, embedded=False)
