@@ -353,6 +353,14 @@ def run_gpu_arm(args):
         g_ms = sum(float(np.sum(agg[t_])) for t_ in gemm_tags) / nprof
         g_fl = sum(fl[t_] * (len(agg[t_]) // nprof) for t_ in gemm_tags)
         achieved = g_fl / (g_ms * 1e-3) / 1e12
+        traffic = None   # DRAM bytes per launch (average over the same launches), from the committed ncu capture
+        tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as fh:
+                tj = json.load(fh)
+            if all(t_ in tj for t_ in gemm_tags):
+                n_l = sum(len(agg[t_]) // nprof for t_ in gemm_tags)
+                traffic = round(sum(tj[t_] * (len(agg[t_]) // nprof) for t_ in gemm_tags) / n_l)
         roofline = {
             "bound": "tensor", "kernel": "vtq::gemm_kernel (encoder QKV/out/fc1/fc2 projections, tcgen05)",
             "achieved": round(achieved, 1), "peak": pk["sustained"], "unit": "TFLOP/s",
@@ -362,7 +370,11 @@ def run_gpu_arm(args):
             "flops_per_step": g_fl, "avg_ms_per_step": round(g_ms, 3), "share_of_step": round(g_ms / step_ms, 4),
             "note": "executed FLOPs of the full-row projection launches (the last block's token-row launches are "
                     "listed separately under kernels as *_tok)",
-            "traffic": None,
+            "traffic": traffic,
+            "algorithmic_bytes_per_launch": round(sum(
+                {"gemm_qkv": rows * HIDDEN * 2 + rows * 3 * HIDDEN * 2, "gemm_out": rows * HIDDEN * 2 + 2 * rows * HIDDEN * 4,
+                 "gemm_fc1": rows * HIDDEN * 2 + rows * MLP * 2, "gemm_fc2": rows * MLP * 2 + 2 * rows * HIDDEN * 4}[t_]
+                * (len(agg[t_]) // nprof) for t_ in gemm_tags) / sum(len(agg[t_]) // nprof for t_ in gemm_tags)),
         }
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample on the host cores

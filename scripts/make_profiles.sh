@@ -10,6 +10,7 @@ python scripts/launch_summary.py gpurun_out/launches.csv > profiles/${R}_launche
 for k in gemm2 attention hbm; do
   python scripts/ncu_summary.py gpurun_out/prof_${k}.ncu-rep > profiles/${R}_ncu_${k}.txt 2>&1
 done
+python scripts/gemm_traffic.py gpurun_out/prof_gemm2.ncu-rep profiles/gemm_traffic.json
 tail -3 gpurun_out/pytest_gpu.log > profiles/${R}_pytest_gpu.txt
 tail -2 gpurun_out/smoke.log > profiles/${R}_smoke.txt
 cat gpurun_out/host.txt > profiles/${R}_host.txt
