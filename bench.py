@@ -28,6 +28,7 @@ import torch  # noqa: E402
 
 H_IMG, W_IMG, N_PATCH, PAIRS = 384, 512, 500, 32
 WORKLOAD = "cfg2: batch 32 pairs 512x384, 500 single-scale 16x16 patches per image, ViT-B/16 + DiffNet"
+WORKLOAD_SWEEP = "cfg5 sweep point: batch {} pairs 512x384, 500 single-scale patches per image, ViT-B/16 + DiffNet"
 HIDDEN, MLP, LAYERS = 768, 3072, 12
 
 
@@ -183,7 +184,7 @@ def run_gpu_arm(args):
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    B = PAIRS  # per GPU (weak scaling: every rank encodes its own 32 pairs)
+    B = args.pairs  # per GPU (weak scaling: every rank encodes its own batch; default = cfg2's 32 pairs)
     model = build_model(dev, args.dtype)
     eng = model.engine
 
@@ -391,7 +392,7 @@ def run_gpu_arm(args):
             "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_gpu": B, "patches": N_PATCH, "image_hw": [H_IMG, W_IMG],
+            "config": {"workload": WORKLOAD if B == PAIRS else WORKLOAD_SWEEP.format(B), "pairs_per_gpu": B, "patches": N_PATCH, "image_hw": [H_IMG, W_IMG],
                        "operands": f"{args.dtype} tcgen05 operands, fp32 accumulate/residual/LN/softmax/DiffNet",
                        "parallelism": f"dp{world} (pairs sharded, weight replicas, score all_gather only)",
                        "cuda_graph": not args.no_graph,
@@ -425,6 +426,8 @@ def main():
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--pairs", type=int, default=PAIRS,
+                    help="pairs per GPU per step (default 32 = BASELINE configs[1]; configs[4] sweeps 256-2048)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
