@@ -381,7 +381,7 @@ def run_gpu_arm(args):
     # ---- CPU baseline (rank 0, N=1 only): bounded sample on the host cores
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        rate, cores, sample = cpu_reference_rate(4, repeats=2)
+        rate, cores, sample = cpu_reference_rate(8, repeats=3)
         cpu = {"value": round(rate, 3), "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample}
 
     if rank == 0:
