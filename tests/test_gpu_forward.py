@@ -297,3 +297,64 @@ def test_forward_from_uint8_images_matches_fp32_images():
         qa = m.forward_from_images(torch.from_numpy(u8).cuda(), smp)
         qb = m.forward_from_images(f32.cuda(), smp)
     assert torch.equal(qa, qb)
+
+
+def _rand_inputs(B, N, P=16, seed=0, scales=None):
+    g = torch.Generator().manual_seed(seed)
+    patches = (torch.randn(B, N, 3, P, P, generator=g), torch.randn(B, N, 3, P, P, generator=g))
+    pos = (torch.rand(B, N, 2, generator=g) * 0.999, torch.rand(B, N, 2, generator=g) * 0.999)
+    sc = None
+    if scales:
+        sc = (torch.randint(0, scales, (B, N), generator=g).float(), torch.randint(0, scales, (B, N), generator=g).float())
+    return patches, pos, sc
+
+
+def _check_against_oracle(m, patches, pos, sc, tol=SCORE_TOL):
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    want = vtamiq_oracle.vtamiq_forward(sd, patches, pos, sc).numpy()
+    m = m.cuda()
+    cu = lambda tup: tuple(t.cuda() for t in tup) if tup is not None else (None, None)
+    with torch.no_grad():
+        q, _ = m(cu(patches), cu(pos), cu(sc))
+    err = np.abs(q.cpu().numpy() - want).max()
+    assert err <= tol, (err, q.cpu().numpy(), want)
+    return err
+
+
+@pytest.mark.parametrize("kw", [dict(diff_scale=False), dict(calibrate=False), dict(num_rgs=2, num_rcabs=3, ca_reduction=4)])
+def test_head_variants_match_oracle(kw):
+    """Constructor switches of the reference VTAMIQ (vtamiq.py:26-46): no LayerScale on the difference, no DiffNet,
+    other DiffNet depths / squeeze ratios."""
+    m = _build(dict(num_keep_layers=2), kw)
+    patches, pos, sc = _rand_inputs(3, 70, seed=3)
+    _check_against_oracle(m, patches, pos, sc)
+
+
+def test_vit_variants_b8_and_l16_match_oracle():
+    """The reference's other ViT variants (transformer.py:81-111): ViT-B/8 (8x8 patches, 48x48 pos grid) through the
+    reference-format forward, ViT-L/16 (hidden 1024, 16 heads, mlp 4096) incl. the device gather."""
+    import vtamiq_b200
+    torch.manual_seed(0)
+    m8 = vtamiq_b200.VTAMIQ(vit_config=dict(pretrained=False, variant=vtamiq_b200.VIT_VARIANT_B8, num_keep_layers=2)).eval()
+    synth.perturb_(m8)
+    patches, pos, sc = _rand_inputs(2, 90, P=8, seed=5)
+    _check_against_oracle(m8, patches, pos, sc)
+    torch.manual_seed(0)
+    mL = vtamiq_b200.VTAMIQ(vit_config=dict(pretrained=False, variant=vtamiq_b200.VIT_VARIANT_L16, num_keep_layers=3)).eval()
+    synth.perturb_(mL)
+    patches, pos, sc = _rand_inputs(2, 130, seed=6)
+    _check_against_oracle(mL, patches, pos, sc)
+
+
+def test_pre_embedded_inputs_and_no_pos_embedding():
+    """Embeddings.forward also accepts already-embedded (B, N, H) inputs (transformer.py:533-534) and can run
+    without positional embeddings (use_pos_embedding=False)."""
+    m = _build(dict(num_keep_layers=2), {})
+    g = torch.Generator().manual_seed(8)
+    emb = (torch.randn(2, 40, 768, generator=g) * 0.3, torch.randn(2, 40, 768, generator=g) * 0.3)
+    pos = (torch.rand(2, 40, 2, generator=g) * 0.999, torch.rand(2, 40, 2, generator=g) * 0.999)
+    _check_against_oracle(m, emb, pos, None)
+    m2 = _build(dict(num_keep_layers=2, use_pos_embedding=False), {})
+    patches, pos, sc = _rand_inputs(2, 40, seed=9)
+    _check_against_oracle(m2, patches, pos, sc)
