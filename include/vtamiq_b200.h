@@ -139,9 +139,12 @@ int vtq_attention_fwd_trace(vtq_ctx* ctx, const void* qkv, void* out, int n_seq,
 
 /* ---- K7: final LayerNorm of the quality token + difference ----------------------------------------
  * replaces encoder_norm on the used token (transformer.py:376,:634) and modules/vtamiq/vtamiq.py:104-111.
- * x [2*B][S][hidden] fp32; diff[b] = gamma * (LN(x[b][token]) - LN(x[B+b][token])); gamma may be NULL. */
-int vtq_cls_diff(vtq_ctx* ctx, const float* x, int B, int S, int hidden, int token, const float* ln_weight,
-                 const float* ln_bias, float eps, const float* gamma, float* diff, void* stream);
+ * x_ref, x_dist [B][S][hidden] fp32 (two blocks of the stacked residual stream; the pairwise mode of train.py:286-287
+ * scores two distorted blocks against ONE encoded reference block);
+ * diff[b] = gamma * (LN(x_ref[b][token]) - LN(x_dist[b][token])); gamma may be NULL. */
+int vtq_cls_diff(vtq_ctx* ctx, const float* x_ref, const float* x_dist, int B, int S, int hidden, int token,
+                 const float* ln_weight, const float* ln_bias, float eps, const float* gamma, float* diff,
+                 void* stream);
 
 /* ---- K8: DiffNet + quality head ------------------------------------------------------------------------
  * replaces modules/RCAN/channel_attention.py:13-86 as instantiated by modules/vtamiq/vtamiq.py:12-23, and the

@@ -358,3 +358,18 @@ def test_pre_embedded_inputs_and_no_pos_embedding():
     m2 = _build(dict(num_keep_layers=2, use_pos_embedding=False), {})
     patches, pos, sc = _rand_inputs(2, 40, seed=9)
     _check_against_oracle(m2, patches, pos, sc)
+
+
+def test_pairwise_shares_the_reference_encoding():
+    """train.predict's pairwise branch (train.py:281-301) scores (ref, dist1) and (ref, dist2) with two model calls;
+    forward_pairwise encodes ref once and must return the same two score vectors."""
+    m = _build(dict(num_keep_layers=3), {}).cuda()
+    B, N = 3, 120
+    g = torch.Generator(device="cuda").manual_seed(31)
+    pr, p1, p2 = (torch.randn(B, N, 3, 16, 16, device="cuda", generator=g) for _ in range(3))
+    sr, s1, s2 = (torch.rand(B, N, 2, device="cuda", generator=g) * 0.999 for _ in range(3))
+    with torch.no_grad():
+        qa, _ = m((pr, p1), (sr, s1), (None, None))
+        qb, _ = m((pr, p2), (sr, s2), (None, None))
+        q1, q2 = m.forward_pairwise((pr, p1, p2), (sr, s1, s2), None)
+    assert torch.allclose(q1, qa, atol=2e-6) and torch.allclose(q2, qb, atol=2e-6)

@@ -214,7 +214,7 @@ def test_cls_diff(ctx):
     w = torch.randn(H, device="cuda", generator=g); b = torch.randn(H, device="cuda", generator=g)
     gamma = torch.rand(H, device="cuda", generator=g) + 0.5
     out = torch.empty(B, H, device="cuda")
-    ctx.call("vtq_cls_diff", P(x), B, S, H, 0, P(w), P(b), 1e-6, P(gamma), P(out), ST())
+    ctx.call("vtq_cls_diff", P(x), C.c_void_p(x.data_ptr() + B * S * H * 4), B, S, H, 0, P(w), P(b), 1e-6, P(gamma), P(out), ST())
     torch.cuda.synchronize()
     ln = torch.nn.functional.layer_norm(x[:, 0].cpu(), (H,), w.cpu(), b.cpu(), 1e-6)
     want = (ln[:B] - ln[B:]) * gamma.cpu()

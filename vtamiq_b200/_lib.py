@@ -36,7 +36,7 @@ SIGNATURES = {
     "vtq_gemm": (_i, [_vp, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i64, _vp, _vp]),
     "vtq_attention_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "vtq_attention_fwd_trace": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
-    "vtq_cls_diff": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp]),
+    "vtq_cls_diff": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp]),
     "vtq_diffnet_head": (_i, [_vp, _vp, C.POINTER(_vp), _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
 }
 

@@ -286,7 +286,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 // Only the quality-token rows need the encoder_norm; 1/sqrt (not rsqrt.approx) keeps this fp32-faithful.
 // ------------------------------------------------------------------------------------------------
 template <int VPL>
-__global__ void __launch_bounds__(128) cls_diff_kernel(const float* __restrict__ x, int B, int S, int token,
+__global__ void __launch_bounds__(128) cls_diff_kernel(const float* __restrict__ x_ref,
+                                                       const float* __restrict__ x_dist, int B, int S, int token,
                                                        const float* __restrict__ w, const float* __restrict__ b,
                                                        float eps, const float* __restrict__ gamma,
                                                        float* __restrict__ diff) {
@@ -297,8 +298,8 @@ __global__ void __launch_bounds__(128) cls_diff_kernel(const float* __restrict__
   float4 y[2][VPL];
 #pragma unroll
   for (int img = 0; img < 2; ++img) {
-    const size_t row = (static_cast<size_t>(img) * B + pair) * S + token;
-    const float4* src = reinterpret_cast<const float4*>(x + row * HIDDEN);
+    const size_t row = static_cast<size_t>(pair) * S + token;
+    const float4* src = reinterpret_cast<const float4*>((img == 0 ? x_ref : x_dist) + row * HIDDEN);
     float4 v[VPL];
     float s = 0.f;
 #pragma unroll
@@ -454,17 +455,17 @@ extern "C" int vtq_layernorm(vtq_ctx* ctx, const float* x, int64_t x_stride, con
   return VTQ_OK;
 }
 
-extern "C" int vtq_cls_diff(vtq_ctx* ctx, const float* x, int B, int S, int hidden, int token,
+extern "C" int vtq_cls_diff(vtq_ctx* ctx, const float* x_ref, const float* x_dist, int B, int S, int hidden, int token,
                             const float* ln_weight, const float* ln_bias, float eps, const float* gamma,
                             float* diff, void* stream) {
   if (!ctx) return VTQ_ERR_INVALID;
-  VTQ_CHECK_ARG(ctx, x && ln_weight && ln_bias && diff, "null pointer");
+  VTQ_CHECK_ARG(ctx, x_ref && x_dist && ln_weight && ln_bias && diff, "null pointer");
   VTQ_CHECK_ARG(ctx, hidden == 768 || hidden == 1024, "hidden must be 768 or 1024");
   VTQ_CHECK_ARG(ctx, B >= 1 && S >= 1 && token >= 0 && token < S, "shape");
   const unsigned blocks = static_cast<unsigned>((B + 3) / 4);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (hidden == 768) cls_diff_kernel<6><<<blocks, 128, 0, st>>>(x, B, S, token, ln_weight, ln_bias, eps, gamma, diff);
-  else cls_diff_kernel<8><<<blocks, 128, 0, st>>>(x, B, S, token, ln_weight, ln_bias, eps, gamma, diff);
+  if (hidden == 768) cls_diff_kernel<6><<<blocks, 128, 0, st>>>(x_ref, x_dist, B, S, token, ln_weight, ln_bias, eps, gamma, diff);
+  else cls_diff_kernel<8><<<blocks, 128, 0, st>>>(x_ref, x_dist, B, S, token, ln_weight, ln_bias, eps, gamma, diff);
   VTQ_CHECK_LAUNCH(ctx, "cls_diff launch");
   return VTQ_OK;
 }

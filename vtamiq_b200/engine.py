@@ -50,11 +50,11 @@ class _LayerPack:
 class _Workspace:
     """Device buffers for one (B, N) problem; allocated once, reused by every forward / graph replay."""
 
-    def __init__(self, eng: "Engine", B: int, N: int):
+    def __init__(self, eng: "Engine", B: int, N: int, streams: int = 2):
         dev, t16 = eng.device, eng.torch16
         H, Mlp, T = eng.hidden, eng.mlp_dim, eng.num_tokens
-        self.B, self.N, self.S = B, N, T + N
-        n_seq = 2 * B
+        self.B, self.N, self.S, self.streams = B, N, T + N, streams
+        n_seq = streams * B   # image blocks stacked as sequences: [ref | dist] or [ref | dist1 | dist2] (pairwise)
         rows, prow = n_seq * self.S, n_seq * N
         e = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt, device=dev)
         self.patches16 = e(prow, eng.patch_elems, dt=t16)
@@ -66,9 +66,10 @@ class _Workspace:
         self.qkv = e(rows, 3 * H, dt=t16)
         self.att = e(rows, H, dt=t16)
         self.h1 = e(rows, Mlp, dt=t16)
-        self.diff = e(B, H)
-        self.q = e(B)
-        self.tail_ws = torch.empty(max(eng.ctx.workspace_bytes(B, H), 16), dtype=torch.uint8, device=dev)
+        self.diff = e((streams - 1) * B, H)
+        self.q = e((streams - 1) * B)
+        self.tail_ws = torch.empty(max(eng.ctx.workspace_bytes((streams - 1) * B, H), 16), dtype=torch.uint8,
+                                   device=dev)
         self.pos_idx = None    # optional int32 dumps for the parity tests
         self.scale_idx = None
         self.graph = None      # captured encoder+tail graph
@@ -214,11 +215,11 @@ class Engine:
         self.token_num = int(getattr(m, "token_num", 0))
 
     # ------------------------------------------------------------------ workspaces
-    def workspace(self, B: int, N: int) -> _Workspace:
+    def workspace(self, B: int, N: int, streams: int = 2) -> _Workspace:
         self._ensure_ready()
-        ws = self._ws.get((B, N))
+        ws = self._ws.get((B, N, streams))
         if ws is None:
-            ws = self._ws[(B, N)] = _Workspace(self, B, N)
+            ws = self._ws[(B, N, streams)] = _Workspace(self, B, N, streams)
         return ws
 
     # ------------------------------------------------------------------ launch sequence
@@ -226,7 +227,7 @@ class Engine:
         """Everything after the inputs sit in ws.patches16 / ws.proj, ws.pos, ws.scales."""
         c, st, dt = self._call, _stream(), self.vtq16
         B, N, S, H = ws.B, ws.N, ws.S, self.hidden
-        n_seq, rows, prow = 2 * B, 2 * B * S, 2 * B * N
+        n_seq, rows, prow = ws.streams * B, ws.streams * B * S, ws.streams * B * N
         if not embedded:
             c("gemm_embed", "vtq_gemm", _ptr(ws.patches16), 0, _ptr(self.w_pe), _ptr(self.b_pe), prow, H,
               self.patch_elems, dt, EPI_BIAS_F32, _ptr(ws.proj), 0, None, st)
@@ -271,10 +272,13 @@ class Engine:
               EPI_BIAS_GELU_H, _ptr(ws.h1), 0, None, st)
             c("gemm_fc2", "vtq_gemm", _ptr(ws.h1), 0, _ptr(L.w_fc2), _ptr(L.b_fc2), rows, H, self.mlp_dim, dt,
               EPI_BIAS_RESID_F32, _ptr(ws.x), 0, _ptr(L.g2), st)
-        c("cls_diff", "vtq_cls_diff", _ptr(ws.x), B, S, H, self.token_num, _ptr(self.lnf_w), _ptr(self.lnf_b), eps,
-          _ptr(self.diff_gamma), _ptr(ws.diff), st)
+        for k in range(1, ws.streams):   # every distorted block against the (once-encoded) reference block
+            c("cls_diff", "vtq_cls_diff", _ptr(ws.x), C.c_void_p(ws.x.data_ptr() + k * B * S * H * 4), B, S, H,
+              self.token_num, _ptr(self.lnf_w), _ptr(self.lnf_b), eps, _ptr(self.diff_gamma),
+              C.c_void_p(ws.diff.data_ptr() + (k - 1) * B * H * 4), st)
+        nq = (ws.streams - 1) * B
         c("diffnet_head", "vtq_diffnet_head", _ptr(ws.diff), self._tail_params, len(self._tail_params), self.num_rgs,
-          self.num_rcabs, H, self.ca_hidden, self.head_hidden, B, _ptr(ws.q), _ptr(ws.tail_ws), st)
+          self.num_rcabs, H, self.ca_hidden, self.head_hidden, nq, _ptr(ws.q), _ptr(ws.tail_ws), st)
 
     def launches_per_forward(self, embedded: bool = False) -> int:
         """Kernels of ours in one encode+score pass (excludes the input staging kernels)."""
@@ -302,7 +306,7 @@ class Engine:
         c, st = self.ctx.call, _stream()
         B, N = ws.B, ws.N
         embedded = patches[0].dim() == 3
-        for img in range(2):
+        for img in range(ws.streams):
             p = patches[img]
             if p.dtype != torch.float32 or not p.is_contiguous():
                 p = p.to(torch.float32).contiguous()

@@ -130,6 +130,24 @@ class VTAMIQ(VisionTransformerBackbone):
             eng.run(ws, embedded)
             return ws.q.clone(), None
 
+    def forward_pairwise(self, patches, pos, scales):
+        """Pairwise mode of ``train.predict`` (train.py:281-301): the reference calls the model twice, once per
+        distorted image, encoding the SAME reference patches both times.  Here the three image blocks go through
+        the encoder once (3B sequences instead of 4B) and both distorted blocks are scored against the shared
+        reference.  patches/pos/scales: 3-tuples (ref, dist1, dist2).  Returns (q1, q2), identical to
+        ``forward((ref, dist1), ...)[0]`` and ``forward((ref, dist2), ...)[0]``."""
+        self._check_inference()
+        eng = self._engine
+        if len(patches) != 3:
+            raise ValueError("forward_pairwise expects (ref, dist1, dist2) tuples")
+        B, N = patches[0].shape[0], patches[0].shape[1]
+        with torch.no_grad():
+            ws = eng.workspace(B, N, streams=3)
+            embedded = eng.stage_patches(ws, patches, pos, scales if scales is not None else (None,) * 3)
+            eng.run(ws, embedded)
+            q = ws.q.clone()
+            return q[:B], q[B:]
+
     # -- fast entry: gather on device ------------------------------------------------------------
     def forward_from_images(self, images, samples, return_inputs=False):
         """Device-side patch extraction fused in front of the forward.
