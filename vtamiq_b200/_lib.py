@@ -10,7 +10,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvtamiq_b200.so")
+# VTQ_LIBRARY overrides the path (A/B runs of two builds of the same ABI); the default is the in-tree build
+LIB_PATH = os.environ.get("VTQ_LIBRARY") or os.path.join(_HERE, "libvtamiq_b200.so")
 
 VTQ_F16, VTQ_BF16 = 0, 1
 EPI_BIAS_H, EPI_BIAS_GELU_H, EPI_BIAS_F32, EPI_BIAS_RESID_F32 = 0, 1, 2, 3
