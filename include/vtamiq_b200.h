@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VTQ_ABI_VERSION 1
+#define VTQ_ABI_VERSION 2
 
 enum vtq_status {
   VTQ_OK = 0,
@@ -121,6 +121,32 @@ int vtq_layernorm(vtq_ctx* ctx, const float* x, int64_t x_stride, const float* w
  * K % 64 == 0, N % 64 == 0; any M >= 1.  ldo in elements of the output type. */
 int vtq_gemm(vtq_ctx* ctx, const void* A, int64_t lda, const void* W, const float* bias, int M, int N, int K,
              int dtype, int epilogue, void* out, int64_t ldo, const float* gamma, void* stream);
+
+/* ---- K3/K5 + K4 folded: the encoder's LayerNorms carried by the GEMMs either side of them -------------
+ * replaces the same lines as vtq_gemm plus the LayerNorm between them (transformer.py:276,:281) without a
+ * separate pass over the fp32 residual stream.  CTA-pair kernel only: M >= 256.  Exactly one side per call:
+ *
+ * produce (ln_out != NULL; epilogue must be VTQ_EPI_BIAS_RESID_F32):
+ *     out32 += gamma * (acc + bias) as a read-add-write of the caller's rows; additionally
+ *     raw16_out [M][N]                    the new rows rounded to 16 bit, NOT normalised
+ *     ln_out    [vtq_gemm_ln_slots(N)][M][2]  per row partial (sum, sum of squares) over a fixed column subset
+ *                                         per slot (deterministic: no atomics); the slots add up to the full row.
+ * consume (ln_in != NULL; epilogue VTQ_EPI_BIAS_H or VTQ_EPI_BIAS_GELU_H):
+ *     A = raw16 rows, ln_in = ln_in_slots slots as written above (or by vtq_rowstats_cast: 1 slot), and the caller
+ *     pre-folds the LayerNorm's affine into the operands:  W'[n][k] = W[n][k] * ln_w[k]   (then rounded to 16 bit),
+ *     bias'[n] = bias[n] + sum_k ln_b[k] W[n][k],  ln_colsum[n] = sum_k W'[n][k]  (of the rounded W').  The kernel
+ *     computes  out16 = epi( rstd_r * (A W'^T - mean_r * ln_colsum) + bias' ),  mean/rstd over K columns with ln_eps,
+ *     which equals epi( LN(x) W^T + bias ). */
+int vtq_gemm_ln(vtq_ctx* ctx, const void* A, int64_t lda, const void* W, const float* bias, int M, int N, int K,
+                int dtype, int epilogue, void* out, int64_t ldo, const float* gamma, const float* ln_in,
+                int ln_in_slots, const float* ln_colsum, float ln_eps, void* raw16_out, float* ln_out,
+                void* stream);
+int vtq_gemm_ln_slots(int N);
+
+/* fp32 rows -> raw 16-bit copy + (sum, sum of squares) per row in slot 0 of ln_out [1][rows][2]: the entry of a
+ * folded-LayerNorm chain (the rows embed_assemble wrote).  hidden 768 or 1024. */
+int vtq_rowstats_cast(vtq_ctx* ctx, const float* x, int64_t rows, int hidden, void* raw16_out, float* ln_out,
+                      int dtype, void* stream);
 
 /* ---- K6: fused multi-head self-attention -----------------------------------------------------------
  * replaces transformer.py:158-166: softmax(Q K^T / sqrt(64)) V per (sequence, head), never materialising S x S.

@@ -193,12 +193,32 @@ def test_last_block_pruning_is_exact():
     g = torch.Generator(device="cuda").manual_seed(2)
     p = (torch.randn(B, N, 3, 16, 16, device="cuda", generator=g), torch.randn(B, N, 3, 16, 16, device="cuda", generator=g))
     pos = (torch.rand(B, N, 2, device="cuda", generator=g), torch.rand(B, N, 2, device="cuda", generator=g))
-    a = _build({}, {}, prune_last_block=True).cuda()
-    b = _build({}, {}, prune_last_block=False).cuda()
+    a = _build({}, {}, prune_last_block=True, fuse_layernorm=False).cuda()
+    b = _build({}, {}, prune_last_block=False, fuse_layernorm=False).cuda()
     with torch.no_grad():
         qa, _ = a(p, pos, (None, None))
         qb, _ = b(p, pos, (None, None))
     assert torch.allclose(qa, qb, atol=2e-5), (qa, qb)
+
+
+@pytest.mark.parametrize("prune", [True, False])
+def test_layernorm_folding_matches_separate_layernorm(prune):
+    """LayerNorms carried by the GEMMs (vtq_gemm_ln) vs the separate LayerNorm kernel: same scores up to the
+    16-bit rounding point moving from LN(x) to x, far inside the parity bar."""
+    B, N = 4, 300
+    g = torch.Generator(device="cuda").manual_seed(7)
+    p = (torch.randn(B, N, 3, 16, 16, device="cuda", generator=g), torch.randn(B, N, 3, 16, 16, device="cuda", generator=g))
+    pos = (torch.rand(B, N, 2, device="cuda", generator=g), torch.rand(B, N, 2, device="cuda", generator=g))
+    a = _build({}, {}, prune_last_block=prune, fuse_layernorm=True).cuda()
+    b = _build({}, {}, prune_last_block=prune, fuse_layernorm=False).cuda()
+    synth.perturb_(a, seed=3)
+    b.load_state_dict(a.state_dict())
+    with torch.no_grad():
+        qa, _ = a(p, pos, (None, None))
+        qb, _ = b(p, pos, (None, None))
+        qa2, _ = a(p, pos, (None, None))
+    assert torch.equal(qa, qa2)                      # fixed statistics slots: deterministic
+    assert (qa - qb).abs().max().item() < 5e-4, (qa, qb)
 
 
 def _pairs(B, H, W, counts, seed):

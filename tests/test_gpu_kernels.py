@@ -95,6 +95,107 @@ def test_gemm_rejects_bad_shapes(ctx):
         ctx.call("vtq_gemm", P(A), 0, P(W), P(b), 128, 128, 100, 0, 0, P(o), 0, None, ST())
 
 
+# ------------------------------------------------------------------------------------------ GEMM + folded LayerNorm
+def _ln_slots(N):
+    from vtamiq_b200 import _lib
+    return int(_lib.load_library().vtq_gemm_ln_slots(N))
+
+
+@pytest.mark.parametrize("dt", ["fp16", "bf16"])
+@pytest.mark.parametrize("M,N,K,use_gamma", [(300, 768, 768, False), (1000, 768, 3072, True), (257, 1024, 1024, True),
+                                             (32064, 768, 768, False)])
+def test_gemm_ln_produce(ctx, dt, M, N, K, use_gamma):
+    """Residual epilogue that also emits the raw 16-bit rows and the per-row (sum, sum of squares) partials."""
+    code, tdt = DT[dt]
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    A = torch.randn(M, K, device="cuda", generator=g).to(tdt)
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(tdt)
+    b = torch.randn(N, device="cuda", generator=g)
+    gamma = torch.rand(N, device="cuda", generator=g) + 0.5 if use_gamma else None
+    x0 = torch.randn(M, N, device="cuda", generator=g) * 2 + 0.3
+    x = x0.clone()
+    slots = _ln_slots(N)
+    raw = torch.full((M, N), float("nan"), device="cuda", dtype=tdt)
+    stats = torch.full((slots, M, 2), float("nan"), device="cuda")
+    ctx.call("vtq_gemm_ln", P(A), 0, P(W), P(b), M, N, K, code, 3, P(x), 0, P(gamma), None, 0, None, 0.0, P(raw),
+             P(stats), ST())
+    torch.cuda.synchronize()
+    base = A.float() @ W.float().t() + b
+    want = x0 + (base * gamma if use_gamma else base)
+    tol = 2e-2 if dt == "bf16" else 2e-3
+    assert (x - want).abs().max().item() < tol
+    assert torch.equal(raw, x.to(tdt))                       # the 16-bit copy is the rounded fp32 row, bit for bit
+    tot = stats.double().sum(0)
+    assert torch.allclose(tot[:, 0], x.double().sum(1), rtol=1e-5, atol=1e-2)
+    assert torch.allclose(tot[:, 1], (x.double() ** 2).sum(1), rtol=1e-5, atol=1e-2)
+
+
+@pytest.mark.parametrize("dt", ["fp16", "bf16"])
+@pytest.mark.parametrize("M,N,K,gelu,slots", [(300, 2304, 768, False, 1), (1000, 3072, 768, True, 8),
+                                              (32064, 2304, 768, False, 8), (515, 4096, 1024, True, 16)])
+def test_gemm_ln_consume(ctx, dt, M, N, K, gelu, slots):
+    """out = epi(LN(x) W^T + b) computed from RAW 16-bit rows, folded weights and per-row statistics."""
+    code, tdt = DT[dt]
+    g = torch.Generator(device="cuda").manual_seed(N + K + slots)
+    x = torch.randn(M, K, device="cuda", generator=g) * 1.7 + 0.4
+    x[:, 5] *= 12.0                                           # an outlier channel, as real ViT streams have
+    ln_w = torch.rand(K, device="cuda", generator=g) + 0.5
+    ln_b = torch.randn(K, device="cuda", generator=g) * 0.2
+    W = torch.randn(N, K, device="cuda", generator=g) * 0.05
+    b = torch.randn(N, device="cuda", generator=g)
+    eps = 1e-6
+    # fold exactly as Engine._pack does
+    Wf = (W * ln_w[None, :]).to(tdt)
+    bf = b + W @ ln_b
+    cs = Wf.float().sum(1).contiguous()
+    # statistics split over `slots` column groups (what the producing GEMM leaves behind)
+    stats = torch.zeros(slots, M, 2, device="cuda")
+    for s_, cols in enumerate(torch.arange(K, device="cuda").chunk(slots)):
+        stats[s_, :, 0] = x[:, cols].sum(1)
+        stats[s_, :, 1] = (x[:, cols] ** 2).sum(1)
+    raw = x.to(tdt)
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=tdt)
+    ctx.call("vtq_gemm_ln", P(raw), 0, P(Wf), P(bf), M, N, K, code, 1 if gelu else 0, P(out), 0, None, P(stats), slots,
+             P(cs), eps, None, None, ST())
+    torch.cuda.synchronize()
+    want = torch.nn.functional.layer_norm(x, (K,), ln_w, ln_b, eps) @ W.t() + b
+    if gelu:
+        want = torch.nn.functional.gelu(want)
+    assert torch.isfinite(out.float()).all()
+    err = (out.float() - want).abs().max().item()
+    assert err < (8e-2 if dt == "bf16" else 8e-3), err
+
+
+def test_rowstats_cast(ctx):
+    for hidden in (768, 1024):
+        x = torch.randn(1003, hidden, device="cuda") * 3 + 0.7
+        raw = torch.empty(1003, hidden, device="cuda", dtype=torch.float16)
+        stats = torch.empty(1, 1003, 2, device="cuda")
+        ctx.call("vtq_rowstats_cast", P(x), 1003, hidden, P(raw), P(stats), 0, ST())
+        torch.cuda.synchronize()
+        assert torch.equal(raw, x.half())
+        assert torch.allclose(stats[0, :, 0], x.sum(1), rtol=1e-5, atol=1e-3)
+        assert torch.allclose(stats[0, :, 1], (x * x).sum(1), rtol=1e-5, atol=1e-2)
+
+
+def test_gemm_ln_rejects_misuse(ctx):
+    from vtamiq_b200._lib import VtqError
+    A = torch.zeros(128, 768, device="cuda", dtype=torch.float16)
+    W = torch.zeros(768, 768, device="cuda", dtype=torch.float16)
+    b = torch.zeros(768, device="cuda")
+    x = torch.zeros(128, 768, device="cuda")
+    raw = torch.zeros(128, 768, device="cuda", dtype=torch.float16)
+    st = torch.zeros(8, 128, 2, device="cuda")
+    with pytest.raises(VtqError, match="M >= 256"):
+        ctx.call("vtq_gemm_ln", P(A), 0, P(W), P(b), 128, 768, 768, 0, 3, P(x), 0, None, None, 0, None, 0.0, P(raw),
+                 P(st), ST())
+    A = torch.zeros(512, 768, device="cuda", dtype=torch.float16)
+    x = torch.zeros(512, 768, device="cuda")
+    with pytest.raises(VtqError, match="exactly one"):
+        ctx.call("vtq_gemm_ln", P(A), 0, P(W), P(b), 512, 768, 768, 0, 3, P(x), 0, None, None, 0, None, 0.0, None,
+                 None, ST())
+
+
 # ------------------------------------------------------------------------------------------ attention
 def _attn_ref(qkv, n_seq, S, heads):
     H = heads * 64

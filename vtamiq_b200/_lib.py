@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("VTQ_LIBRARY") or os.path.join(_HERE, "libvtamiq_b200.
 
 VTQ_F16, VTQ_BF16 = 0, 1
 EPI_BIAS_H, EPI_BIAS_GELU_H, EPI_BIAS_F32, EPI_BIAS_RESID_F32 = 0, 1, 2, 3
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
@@ -35,6 +35,9 @@ SIGNATURES = {
     "vtq_embed_assemble": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "vtq_layernorm": (_i, [_vp, _vp, _i64, _vp, _vp, _f, _i64, _i, _vp, _i, _vp]),
     "vtq_gemm": (_i, [_vp, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i64, _vp, _vp]),
+    "vtq_gemm_ln": (_i, [_vp, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i64, _vp, _vp, _i, _vp, _f, _vp, _vp, _vp]),
+    "vtq_gemm_ln_slots": (_i, [_i]),
+    "vtq_rowstats_cast": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _i, _vp]),
     "vtq_attention_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "vtq_attention_fwd_trace": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "vtq_cls_diff": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp]),

@@ -37,7 +37,7 @@ int check_cuda(vtq_ctx* ctx, cudaError_t e, const char* what) {
 }
 
 int make_tensor_map(vtq_ctx* ctx, CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base,
-                    const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+                    const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, bool swizzle_64b) {
   cuuint64_t gdims[5];
   cuuint64_t gstrides[4];
   cuuint32_t gbox[5];
@@ -49,7 +49,8 @@ int make_tensor_map(vtq_ctx* ctx, CUtensorMap* out, CUtensorMapDataType dt, int 
     if (i > 0) gstrides[i - 1] = strides_bytes[i - 1];
   }
   CUresult r = ctx->encode_tiled(out, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdims, gstrides,
-                                 gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 swizzle_64b ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];
@@ -120,6 +121,18 @@ extern "C" int vtq_gemm(vtq_ctx* ctx, const void* A, int64_t lda, const void* W,
   return launch_gemm(ctx, A, lda, W, bias, M, N, K, dtype, epilogue, out, ldo, gamma,
                      static_cast<cudaStream_t>(stream));
 }
+
+extern "C" int vtq_gemm_ln(vtq_ctx* ctx, const void* A, int64_t lda, const void* W, const float* bias, int M, int N,
+                           int K, int dtype, int epilogue, void* out, int64_t ldo, const float* gamma,
+                           const float* ln_in, int ln_in_slots, const float* ln_colsum, float ln_eps,
+                           void* raw16_out, float* ln_out, void* stream) {
+  if (!ctx) return VTQ_ERR_INVALID;
+  GemmLnArgs ln = {ln_in, ln_in_slots, ln_colsum, ln_eps, raw16_out, ln_out};
+  return launch_gemm(ctx, A, lda, W, bias, M, N, K, dtype, epilogue, out, ldo, gamma,
+                     static_cast<cudaStream_t>(stream), &ln);
+}
+
+extern "C" int vtq_gemm_ln_slots(int N) { return N >= 64 ? gemm_ln_slots(N) : 0; }
 
 extern "C" int vtq_attention_fwd(vtq_ctx* ctx, const void* qkv, void* out, int n_seq, int S, int heads, int dtype,
                                  int q_rows, void* stream) {

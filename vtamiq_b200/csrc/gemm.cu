@@ -17,7 +17,17 @@
 //                                LayerScale in registers, 128B-swizzled staging in smem, per-warp TMA store —
 //                                or TMA reduce-add for the fp32 residual stream, so the residual
 //                                read-modify-write never travels through the SM.
-// Replaces the ATen addmm/conv calls listed in include/vtamiq_b200.h (vtq_gemm).
+//
+// LayerNorm folding (vtq_gemm_ln, CTA-pair kernel only).  The encoder's LayerNorms sit between a GEMM that
+// updates the fp32 residual stream and a GEMM that consumes the normalised rows; as separate kernels they re-read
+// the stream from HBM.  Folded:
+//   producer (LN = 2, out-projection / fc2): the epilogue reads its rows of x (256-bit loads, prefetched before the
+//       accumulator is waited for), adds, writes x back, writes a RAW 16-bit copy of the new rows, and leaves each
+//       row's partial (sum, sum of squares) over its column chunk in a per-(N-tile, half) slot — fixed slots, no
+//       atomics, so the statistics are deterministic;
+//   consumer (LN = 1, QKV / fc1): A is the raw 16-bit copy, W is pre-scaled by the LayerNorm weight, and the
+//       epilogue applies  y = rstd_r * (acc - mean_r * colsum_n) + bias'_n  (algebraically LN(x) W^T + b).
+// Replaces the ATen addmm/conv calls listed in include/vtamiq_b200.h (vtq_gemm, vtq_gemm_ln).
 #include <cstdlib>
 
 #include "common.cuh"
@@ -33,6 +43,32 @@ constexpr int GEMM_STAGING_BYTES = GEMM_EPI_WARPS * 4096;  // one 32-row x 128 B
 constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;
 
 enum : int { EPI_H = 0, EPI_F32 = 1 };
+enum : int { LN_NONE = 0, LN_CONSUME = 1, LN_PRODUCE = 2 };
+
+// LayerNorm folding arguments (by value in the kernel parameter block; unused fields are null / 0).
+struct LnFold {
+  const float* in;      // consumer: [in_slots][M][2] partial (sum, sum of squares) of the A rows
+  const float* colsum;  // consumer: [N]  sum_k W'[n][k]
+  float* out;           // producer: [2 * ceil(N / BN)][M][2]
+  void* raw16;          // producer: [M][N] 16-bit copy of the new fp32 rows
+  float* x;             // producer: the fp32 residual rows (read-add-write), row stride ldx
+  long long ldx;
+  int in_slots;
+  float eps;
+  float inv_dim;        // consumer: 1 / K
+};
+
+// streaming 16-byte global load (the residual rows are read once per GEMM: keep them out of L1)
+__device__ __forceinline__ float4 ldg_f4_stream(const float* p) {
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 
 // erf-GELU on two values at once, fp32 throughout (packed FFMA2).  erf(z) = z * P(u), u = z^2 * (2/3.5^2) - 1,
 // P = degree-12 Chebyshev fit of erf(z)/z on |z| <= 3.5 re-expanded in u (well conditioned on [-1,1]);
@@ -62,11 +98,12 @@ __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
 // (`half` = 0/1: the two warps sharing a lane quarter interleave chunks).  The caller signals "accumulator free"
 // after this returns (all TMEM reads of the warp are complete by then).
 // ------------------------------------------------------------------------------------------------
-template <int DT, int BN, int EPI, bool GELU>
+template <int DT, int BN, int EPI, bool GELU, int LN = LN_NONE>
 __device__ __forceinline__ void epilogue_tile(uint32_t t_row, int row0, int n0, int N, const float* __restrict__ bias,
                                               const float* __restrict__ gamma, int accumulate,
                                               const CUtensorMap* tmO, uint8_t* buf, int lane, int half,
-                                              uint64_t hint_o) {
+                                              uint64_t hint_o, const float* __restrict__ colsum = nullptr,
+                                              float ln_a = 1.f, float ln_b = 0.f) {
   const uint32_t swz = static_cast<uint32_t>(lane & 7);
   if constexpr (EPI == EPI_F32) {
     // 32 fp32 columns (128 B per row) per staged box
@@ -121,14 +158,29 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_row, int row0, int n0, 
           const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + ncol + hh * 32) + 2 * j);
           const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + ncol + hh * 32) + 2 * j + 1);
           float v[8];
-          v[0] = __uint_as_float(r[8 * j + 0]) + b0.x;
-          v[1] = __uint_as_float(r[8 * j + 1]) + b0.y;
-          v[2] = __uint_as_float(r[8 * j + 2]) + b0.z;
-          v[3] = __uint_as_float(r[8 * j + 3]) + b0.w;
-          v[4] = __uint_as_float(r[8 * j + 4]) + b1.x;
-          v[5] = __uint_as_float(r[8 * j + 5]) + b1.y;
-          v[6] = __uint_as_float(r[8 * j + 6]) + b1.z;
-          v[7] = __uint_as_float(r[8 * j + 7]) + b1.w;
+          if constexpr (LN == LN_CONSUME) {
+            // LayerNorm of the A rows folded in: rstd * (acc - mean * colsum) + bias' = a*acc + (b*colsum + bias')
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(colsum + ncol + hh * 32) + 2 * j);
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(colsum + ncol + hh * 32) + 2 * j + 1);
+            const f32x2 a2 = f2_pack(ln_a, ln_a), b2 = f2_pack(ln_b, ln_b);
+            f2_unpack(f2_fma(a2, f2_pack(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1])),
+                             f2_fma(b2, f2_pack(g0.x, g0.y), f2_pack(b0.x, b0.y))), v[0], v[1]);
+            f2_unpack(f2_fma(a2, f2_pack(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])),
+                             f2_fma(b2, f2_pack(g0.z, g0.w), f2_pack(b0.z, b0.w))), v[2], v[3]);
+            f2_unpack(f2_fma(a2, f2_pack(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])),
+                             f2_fma(b2, f2_pack(g1.x, g1.y), f2_pack(b1.x, b1.y))), v[4], v[5]);
+            f2_unpack(f2_fma(a2, f2_pack(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])),
+                             f2_fma(b2, f2_pack(g1.z, g1.w), f2_pack(b1.z, b1.w))), v[6], v[7]);
+          } else {
+            v[0] = __uint_as_float(r[8 * j + 0]) + b0.x;
+            v[1] = __uint_as_float(r[8 * j + 1]) + b0.y;
+            v[2] = __uint_as_float(r[8 * j + 2]) + b0.z;
+            v[3] = __uint_as_float(r[8 * j + 3]) + b0.w;
+            v[4] = __uint_as_float(r[8 * j + 4]) + b1.x;
+            v[5] = __uint_as_float(r[8 * j + 5]) + b1.y;
+            v[6] = __uint_as_float(r[8 * j + 6]) + b1.z;
+            v[7] = __uint_as_float(r[8 * j + 7]) + b1.w;
+          }
           if constexpr (GELU) {
 #pragma unroll
             for (int e = 0; e < 8; e += 2) gelu_erf2(v[e], v[e + 1]);
@@ -146,6 +198,108 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_row, int row0, int n0, 
       }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Residual epilogue with LayerNorm statistics (LN_PRODUCE): one thread = one row; per 32-column chunk
+//   x_new = x_old + (acc + bias) * gamma   -> fp32 back to x, 16-bit copy to raw16, (sum, sum of squares) kept.
+// x_old of the first chunk arrives in `xo` (loaded before the accumulator was waited for); the next chunk's is
+// requested before the current one is consumed.  Global accesses are 32 B per lane (LDG/STG.256): every lane
+// streams through its own 128 B line, whole sectors only.
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+struct LnProduce {
+  static constexpr int CHUNKS = BN / 64;  // 32-column chunks per epilogue warp (the two warps of a lane quarter interleave)
+};
+
+// x_old of every chunk this warp will touch in the tile, requested before the accumulator barrier is waited for so
+// the HBM round trip overlaps the tile's mainloop.  Coalesced: instruction j covers rows 4j..4j+3 of the warp's 32,
+// eight lanes per 128-byte row segment.
+template <int BN>
+__device__ __forceinline__ void resid_ln_prefetch(const float* __restrict__ x, long long ldx, int row_base, int M,
+                                                  int n0, int N, int half, int lane,
+                                                  float4 (&xp)[LnProduce<BN>::CHUNKS][8]) {
+#pragma unroll
+  for (int i = 0; i < LnProduce<BN>::CHUNKS; ++i) {
+    const int ncol = n0 + (half + 2 * i) * 32;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int r = row_base + 4 * j + (lane >> 3);
+      if (ncol < N && r < M) xp[i][j] = ldg_f4_stream(x + static_cast<size_t>(r) * ldx + ncol + (lane & 7) * 4);
+      else xp[i][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Residual epilogue with LayerNorm statistics (LN_PRODUCE), one thread = one row, per 32-column chunk:
+//   x_new = x_old + (acc + bias) * gamma  -> fp32 box back to x, 16-bit box to raw16, (sum, sum of squares) kept.
+// The prefetched x_old chunk is transposed through the fp32 staging box (written in the TMA swizzle, so the same
+// box is then updated in place and stored by TMA); the 16-bit copy goes through a second, 2 KB staging box.
+// ------------------------------------------------------------------------------------------------
+template <int DT, int BN>
+__device__ __forceinline__ void epilogue_resid_ln(uint32_t t_row, bool row_ok, int row0, int n0, int N,
+                                                  const float* __restrict__ bias, const float* __restrict__ gamma,
+                                                  const CUtensorMap* tmX, const CUtensorMap* tmR, uint8_t* buf_x,
+                                                  uint8_t* buf_r, float2* stats, int half, int lane,
+                                                  float4 (&xp)[LnProduce<BN>::CHUNKS][8]) {
+  const uint32_t bx = smem_u32(buf_x), br = smem_u32(buf_r);
+  const uint32_t swz = static_cast<uint32_t>(lane & 7);
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < LnProduce<BN>::CHUNKS; ++i) {
+    const int c = half + 2 * i;
+    const int ncol = n0 + c * 32;
+    if (ncol >= N) break;
+    uint32_t r[32];
+    tmem_ld32(t_row + c * 32, r);
+    if (lane == 0) tma_wait_group_read<0>();  // the previous stores have finished reading both staging boxes
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {  // coalesced layout -> box rows
+      const uint32_t rr = static_cast<uint32_t>(4 * j + (lane >> 3));
+      st_shared_v4(bx + rr * 128 + (((static_cast<uint32_t>(lane) & 7) ^ (rr & 7)) << 4), __float_as_uint(xp[i][j].x),
+                   __float_as_uint(xp[i][j].y), __float_as_uint(xp[i][j].z), __float_as_uint(xp[i][j].w));
+    }
+    __syncwarp();
+    tmem_wait_ld();
+    const uint32_t row_addr = bx + lane * 128;
+    uint32_t h[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t a = row_addr + ((static_cast<uint32_t>(j) ^ swz) << 4);
+      const float4 xo = ld_shared_f4(a);
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + ncol) + j);
+      float v0 = __uint_as_float(r[4 * j + 0]) + bv.x;
+      float v1 = __uint_as_float(r[4 * j + 1]) + bv.y;
+      float v2 = __uint_as_float(r[4 * j + 2]) + bv.z;
+      float v3 = __uint_as_float(r[4 * j + 3]) + bv.w;
+      if (gamma != nullptr) {
+        const float4 gv = __ldg(reinterpret_cast<const float4*>(gamma + ncol) + j);
+        v0 *= gv.x; v1 *= gv.y; v2 *= gv.z; v3 *= gv.w;
+      }
+      v0 += xo.x; v1 += xo.y; v2 += xo.z; v3 += xo.w;
+      s1 += (v0 + v1) + (v2 + v3);
+      s2 = fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, fmaf(v3, v3, s2))));
+      st_shared_v4(a, __float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2), __float_as_uint(v3));
+      h[2 * j] = pack2<DT>(v0, v1);
+      h[2 * j + 1] = pack2<DT>(v2, v3);
+    }
+    // 16-bit box: dense rows of 64 B under the 64-byte swizzle (16-byte chunk index ^= address bits 7..8)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t o = static_cast<uint32_t>(lane) * 64 + k * 16;
+      st_shared_v4(br + (o ^ (((o >> 7) & 3) << 4)), h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tmX, buf_x, ncol, row0);
+      tma_store_2d(tmR, buf_r, ncol, row0);
+      tma_commit_group();
+    }
+  }
+  if (row_ok) *stats = make_float2(s1, s2);
 }
 
 // ================================================================================================
@@ -349,30 +503,32 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
 }
 
-template <int BN>
+template <int BN, int LN>
 struct Gemm2Cfg {
   static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;  // this CTA's half of the W tile
   static constexpr int STAGE_BYTES = GEMM_A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 128) ? 8 : 6;
+  // LN_PRODUCE adds a 2 KB 16-bit staging box per epilogue warp (behind the 4 KB fp32 boxes)
+  static constexpr int STAGING_BYTES = GEMM_STAGING_BYTES + (LN == LN_PRODUCE ? GEMM_EPI_WARPS * 2048 : 0);
+  static constexpr int STAGES = (LN == LN_PRODUCE) ? ((BN == 128) ? 7 : (BN == 192 ? 6 : 5)) : ((BN == 128) ? 8 : 6);
   static constexpr int ACC_STRIDE = (BN > 128) ? 256 : 128;
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_STAGING_BYTES + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256;
   static_assert(STAGE_BYTES % 1024 == 0, "stage bases must stay 1024 B aligned");
   static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
 };
 
-template <int DT, int BN, int EPI, bool GELU>
+template <int DT, int BN, int EPI, bool GELU, int LN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmO, const float* __restrict__ bias,
-                 const float* __restrict__ gamma, int M, int N, int K, int accumulate, uint64_t hint_a,
-                 uint64_t hint_o) {
-  using Cfg = Gemm2Cfg<BN>;
+                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
+                 const float* __restrict__ bias, const float* __restrict__ gamma, int M, int N, int K, int accumulate,
+                 uint64_t hint_a, uint64_t hint_o, const LnFold ln) {
+  using Cfg = Gemm2Cfg<BN, LN>;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* ring = smem;
   uint8_t* staging = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + GEMM_STAGING_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
   uint64_t* full_bar = bars;                          // [STAGES]  used in the leader; both CTAs' TMA credit it
   uint64_t* empty_bar = bars + Cfg::STAGES;           // [STAGES]  per CTA; arrived by the leader's multicast commit
   uint64_t* acc_full = bars + 2 * Cfg::STAGES;        // [2]       per CTA; multicast commit
@@ -471,11 +627,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
       const int m0 = (t / num_n) * (2 * GEMM_BM) + static_cast<int>(rank) * GEMM_BM;
       const int n0 = (t % num_n) * BN;
       const uint32_t acc = it & 1;
+      const int row = m0 + lane_grp * 32 + lane;  // this thread's output row (= its TMEM lane)
+      const bool row_ok = row < M;
+      // operands of the folded LayerNorm are requested BEFORE the accumulator is waited for
+      float ln_a = 1.f, ln_b = 0.f;
+      float4 xp[LN == LN_PRODUCE ? LnProduce<BN>::CHUNKS : 1][8];
+      if constexpr (LN == LN_CONSUME) {
+        float s1 = 0.f, s2 = 0.f;
+        if (row_ok) {
+          for (int sl = 0; sl < ln.in_slots; ++sl) {
+            const float2 p = __ldg(reinterpret_cast<const float2*>(ln.in) + static_cast<size_t>(sl) * M + row);
+            s1 += p.x;
+            s2 += p.y;
+          }
+        }
+        const float mean = s1 * ln.inv_dim;
+        const float var = fmaxf(s2 * ln.inv_dim - mean * mean, 0.f);
+        ln_a = 1.0f / sqrtf(var + ln.eps);
+        ln_b = -ln_a * mean;
+      }
+      if constexpr (LN == LN_PRODUCE) {
+        resid_ln_prefetch<BN>(ln.x, ln.ldx, m0 + lane_grp * 32, M, n0, N, half, lane, xp);
+      }
       mbar_wait(&acc_full[acc], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + acc * Cfg::ACC_STRIDE;
-      epilogue_tile<DT, BN, EPI, GELU>(t_row, m0 + lane_grp * 32, n0, N, bias, gamma, accumulate, &tmO, my_staging,
-                                       lane, half, hint_o);
+      if constexpr (LN == LN_PRODUCE) {
+        float2* stats = reinterpret_cast<float2*>(ln.out) + static_cast<size_t>((t % num_n) * 2 + half) * M + row;
+        uint8_t* my_raw = staging + GEMM_STAGING_BYTES + (warp - 2) * 2048;
+        epilogue_resid_ln<DT, BN>(t_row, row_ok, m0 + lane_grp * 32, n0, N, bias, gamma, &tmO, &tmR, my_staging, my_raw,
+                                  stats, half, lane, xp);
+      } else {
+        epilogue_tile<DT, BN, EPI, GELU, LN>(t_row, m0 + lane_grp * 32, n0, N, bias, gamma, accumulate, &tmO,
+                                             my_staging, lane, half, hint_o, ln.colsum, ln_a, ln_b);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&acc_empty[acc], 0);  // one arrival per epilogue warp, on the leader
@@ -512,12 +697,12 @@ static int launch_1cta(vtq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& 
   return VTQ_OK;
 }
 
-template <int DT, int BN, int EPI, bool GELU>
+template <int DT, int BN, int EPI, bool GELU, int LN>
 static int launch_2cta(vtq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
-                       const float* bias, const float* gamma, int M, int N, int K, int accumulate,
-                       uint64_t hint_a, uint64_t hint_o, cudaStream_t st) {
-  using Cfg = Gemm2Cfg<BN>;
-  auto kern = gemm2_kernel<DT, BN, EPI, GELU>;
+                       const CUtensorMap& tmR, const float* bias, const float* gamma, int M, int N, int K,
+                       int accumulate, uint64_t hint_a, uint64_t hint_o, const LnFold& ln, cudaStream_t st) {
+  using Cfg = Gemm2Cfg<BN, LN>;
+  auto kern = gemm2_kernel<DT, BN, EPI, GELU, LN>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -527,15 +712,21 @@ static int launch_2cta(vtq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& 
   const int num_tiles = ((M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * ((N + BN - 1) / BN);
   const int max_pairs = ctx->num_sms / 2;
   const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;
-  cudaError_t le = launch_pdl(kern, dim3(2 * pairs), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, st, tmA, tmB, tmO, bias,
-                              gamma, M, N, K, accumulate, hint_a, hint_o);
+  cudaError_t le = launch_pdl(kern, dim3(2 * pairs), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, st, tmA, tmB, tmO, tmR, bias,
+                              gamma, M, N, K, accumulate, hint_a, hint_o, ln);
   if (le != cudaSuccess) return check_cuda(ctx, le, "gemm2 launch");
   VTQ_CHECK_LAUNCH(ctx, "gemm2 launch");
   return VTQ_OK;
 }
 
+int gemm_ln_slots(int N) {
+  const int BN = (N % 256 == 0 && N >= 1536) ? 256 : (N % 192 == 0 ? 192 : 128);  // CTA-pair tile width, as below
+  return 2 * ((N + BN - 1) / BN);
+}
+
 int launch_gemm(vtq_ctx* ctx, const void* A, int64_t lda, const void* W, const float* bias, int M, int N, int K,
-                int dtype, int epilogue, void* out, int64_t ldo, const float* gamma, cudaStream_t st) {
+                int dtype, int epilogue, void* out, int64_t ldo, const float* gamma, cudaStream_t st,
+                const GemmLnArgs* lnargs) {
   VTQ_CHECK_ARG(ctx, A && W && bias && out, "null pointer");
   VTQ_CHECK_ARG(ctx, M >= 1 && N >= 64 && K >= 64, "empty problem");
   VTQ_CHECK_ARG(ctx, K % GEMM_BK == 0, "K must be a multiple of 64");
@@ -556,7 +747,39 @@ int launch_gemm(vtq_ctx* ctx, const void* A, int64_t lda, const void* W, const f
     const char* e = std::getenv("VTQ_GEMM_1CTA");
     return e != nullptr && e[0] == '1';
   }();
-  const bool two_cta = !force_1cta && M >= 2 * GEMM_BM;
+  const bool two_cta = (!force_1cta || lnargs != nullptr) && M >= 2 * GEMM_BM;
+  LnFold ln = {};
+  int ln_mode = LN_NONE;
+  if (lnargs != nullptr) {
+    VTQ_CHECK_ARG(ctx, two_cta, "vtq_gemm_ln needs M >= 256 (CTA-pair kernel)");
+    VTQ_CHECK_ARG(ctx, (lnargs->ln_in != nullptr) != (lnargs->ln_out != nullptr),
+                  "exactly one of ln_in (consume) / ln_out (produce) must be given");
+    if (lnargs->ln_in != nullptr) {
+      VTQ_CHECK_ARG(ctx, epilogue == VTQ_EPI_BIAS_H || epilogue == VTQ_EPI_BIAS_GELU_H,
+                    "LayerNorm consumption needs a 16-bit epilogue");
+      VTQ_CHECK_ARG(ctx, lnargs->ln_colsum != nullptr && lnargs->ln_in_slots >= 1, "ln_colsum / ln_in_slots");
+      VTQ_CHECK_ARG(ctx, reinterpret_cast<uintptr_t>(lnargs->ln_colsum) % 16 == 0 &&
+                             reinterpret_cast<uintptr_t>(lnargs->ln_in) % 8 == 0, "ln_in / ln_colsum alignment");
+      ln.in = lnargs->ln_in;
+      ln.in_slots = lnargs->ln_in_slots;
+      ln.colsum = lnargs->ln_colsum;
+      ln.eps = lnargs->ln_eps;
+      ln.inv_dim = 1.0f / static_cast<float>(K);
+      ln_mode = LN_CONSUME;
+    } else {
+      VTQ_CHECK_ARG(ctx, epilogue == VTQ_EPI_BIAS_RESID_F32, "LayerNorm statistics need the residual epilogue");
+      VTQ_CHECK_ARG(ctx, lnargs->raw16_out != nullptr, "raw16_out is required with ln_out");
+      VTQ_CHECK_ARG(ctx, reinterpret_cast<uintptr_t>(lnargs->raw16_out) % 32 == 0 &&
+                             reinterpret_cast<uintptr_t>(out) % 32 == 0 && ldo % 8 == 0 && N % 32 == 0 &&
+                             reinterpret_cast<uintptr_t>(lnargs->ln_out) % 8 == 0,
+                    "residual / raw16 rows must be 32-byte aligned");
+      ln.out = lnargs->ln_out;
+      ln.raw16 = lnargs->raw16_out;
+      ln.x = static_cast<float*>(out);
+      ln.ldx = ldo;
+      ln_mode = LN_PRODUCE;
+    }
+  }
   // Tile width: 256 for the wide projections (QKV, fc1); N = 768 (attn.out, fc2, patch embed) splits into
   // 4 x 192 under the CTA-pair kernel (504 pair-tiles on 74 pairs = 97 % wave efficiency; 3 x 256 gives 85 %).
   int BN;
@@ -586,6 +809,14 @@ int launch_gemm(vtq_ctx* ctx, const void* A, int64_t lda, const void* W, const f
     int rc = make_tensor_map(ctx, &tmO, out32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : dt16, 2, out, dims, strides, box);
     if (rc) return rc;
   }
+  CUtensorMap tmR = tmO;  // 16-bit copy of the residual rows (LN_PRODUCE only): 32 x 32 boxes, 64-byte rows
+  if (ln_mode == LN_PRODUCE) {
+    uint64_t dims[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M)};
+    uint64_t strides[1] = {static_cast<uint64_t>(N) * 2};
+    uint32_t box[2] = {32u, 32u};
+    int rc = make_tensor_map(ctx, &tmR, dt16, 2, ln.raw16, dims, strides, box, /*swizzle_64b=*/true);
+    if (rc) return rc;
+  }
   const int acc = epilogue == VTQ_EPI_BIAS_RESID_F32 ? 1 : 0;
   if (epilogue != VTQ_EPI_BIAS_RESID_F32) gamma = nullptr;
   // L2 residency plan: the fp32 residual stream x (98 MB at cfg2) is the one buffer every block
@@ -598,22 +829,35 @@ int launch_gemm(vtq_ctx* ctx, const void* A, int64_t lda, const void* W, const f
     else if (epilogue != VTQ_EPI_BIAS_F32) { hint_o = L2_EVICT_FIRST; }
   }
 
-#define VTQ_GEMM_EPI(FN, DTV, BNV)                                                                          \
-  switch (epilogue) {                                                                                       \
-    case VTQ_EPI_BIAS_H: return FN<DTV, BNV, EPI_H, false>(ctx, tmA, tmB, tmO, bias, gamma, M, N, K, 0, hint_a, hint_o, st); \
-    case VTQ_EPI_BIAS_GELU_H: return FN<DTV, BNV, EPI_H, true>(ctx, tmA, tmB, tmO, bias, gamma, M, N, K, 0, hint_a, hint_o, st); \
-    default: return FN<DTV, BNV, EPI_F32, false>(ctx, tmA, tmB, tmO, bias, gamma, M, N, K, acc, hint_a, hint_o, st);        \
+#define VTQ_GEMM_EPI(DTV, BNV)                                                                                     \
+  switch (epilogue) {                                                                                              \
+    case VTQ_EPI_BIAS_H: return launch_1cta<DTV, BNV, EPI_H, false>(ctx, tmA, tmB, tmO, bias, gamma, M, N, K, 0, hint_a, hint_o, st); \
+    case VTQ_EPI_BIAS_GELU_H: return launch_1cta<DTV, BNV, EPI_H, true>(ctx, tmA, tmB, tmO, bias, gamma, M, N, K, 0, hint_a, hint_o, st); \
+    default: return launch_1cta<DTV, BNV, EPI_F32, false>(ctx, tmA, tmB, tmO, bias, gamma, M, N, K, acc, hint_a, hint_o, st);        \
   }
-#define VTQ_GEMM_DT(FN, BNV)                                     \
-  if (dtype == VTQ_F16) { VTQ_GEMM_EPI(FN, DT_F16, BNV) } else { VTQ_GEMM_EPI(FN, DT_BF16, BNV) }
+#define VTQ_GEMM2_EPI(DTV, BNV)                                                                                    \
+  switch (epilogue) {                                                                                              \
+    case VTQ_EPI_BIAS_H:                                                                                           \
+      if (ln_mode == LN_CONSUME) return launch_2cta<DTV, BNV, EPI_H, false, LN_CONSUME>(ctx, tmA, tmB, tmO, tmR, bias, gamma, M, N, K, 0, hint_a, hint_o, ln, st); \
+      return launch_2cta<DTV, BNV, EPI_H, false, LN_NONE>(ctx, tmA, tmB, tmO, tmR, bias, gamma, M, N, K, 0, hint_a, hint_o, ln, st); \
+    case VTQ_EPI_BIAS_GELU_H:                                                                                      \
+      if (ln_mode == LN_CONSUME) return launch_2cta<DTV, BNV, EPI_H, true, LN_CONSUME>(ctx, tmA, tmB, tmO, tmR, bias, gamma, M, N, K, 0, hint_a, hint_o, ln, st); \
+      return launch_2cta<DTV, BNV, EPI_H, true, LN_NONE>(ctx, tmA, tmB, tmO, tmR, bias, gamma, M, N, K, 0, hint_a, hint_o, ln, st); \
+    default:                                                                                                       \
+      if (ln_mode == LN_PRODUCE) return launch_2cta<DTV, BNV, EPI_F32, false, LN_PRODUCE>(ctx, tmA, tmB, tmO, tmR, bias, gamma, M, N, K, acc, hint_a, hint_o, ln, st); \
+      return launch_2cta<DTV, BNV, EPI_F32, false, LN_NONE>(ctx, tmA, tmB, tmO, tmR, bias, gamma, M, N, K, acc, hint_a, hint_o, ln, st); \
+  }
+#define VTQ_GEMM_DT(MACRO, BNV)                                  \
+  if (dtype == VTQ_F16) { MACRO(DT_F16, BNV) } else { MACRO(DT_BF16, BNV) }
   if (two_cta) {
-    if (BN == 256) { VTQ_GEMM_DT(launch_2cta, 256) }
-    if (BN == 192) { VTQ_GEMM_DT(launch_2cta, 192) }
-    VTQ_GEMM_DT(launch_2cta, 128)
+    if (BN == 256) { VTQ_GEMM_DT(VTQ_GEMM2_EPI, 256) }
+    if (BN == 192) { VTQ_GEMM_DT(VTQ_GEMM2_EPI, 192) }
+    VTQ_GEMM_DT(VTQ_GEMM2_EPI, 128)
   } else {
-    if (BN == 256) { VTQ_GEMM_DT(launch_1cta, 256) }
-    VTQ_GEMM_DT(launch_1cta, 128)
+    if (BN == 256) { VTQ_GEMM_DT(VTQ_GEMM_EPI, 256) }
+    VTQ_GEMM_DT(VTQ_GEMM_EPI, 128)
   }
+#undef VTQ_GEMM2_EPI
 #undef VTQ_GEMM_DT
 #undef VTQ_GEMM_EPI
 }

@@ -29,7 +29,8 @@ int check_cuda(vtq_ctx* ctx, cudaError_t e, const char* what);
 
 // dims/strides innermost-first; strides in BYTES for dims 1..rank-1; all tiles use 128B swizzle.
 int make_tensor_map(vtq_ctx* ctx, CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base,
-                    const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
+                    const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                    bool swizzle_64b = false);  // default: 128-byte swizzle (inner box extent of 128 bytes)
 
 inline CUtensorMapDataType tm_dtype16(int dtype) {
   return dtype == VTQ_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -69,8 +70,19 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
 }
 
 // per-kernel launchers (defined next to their kernels)
+// LayerNorm folding around a GEMM (vtq_gemm_ln): exactly one of ln_in (consume) / ln_out (produce) is set
+struct GemmLnArgs {
+  const float* ln_in;      // [ln_in_slots][M][2] partial (sum, sum of squares) of the A rows
+  int ln_in_slots;
+  const float* ln_colsum;  // [N]
+  float ln_eps;
+  void* raw16_out;         // [M][N]
+  float* ln_out;           // [gemm_ln_slots(N)][M][2]
+};
+int gemm_ln_slots(int N);
 int launch_gemm(vtq_ctx* ctx, const void* A, int64_t lda, const void* W, const float* bias, int M, int N, int K,
-                int dtype, int epilogue, void* out, int64_t ldo, const float* gamma, cudaStream_t st);
+                int dtype, int epilogue, void* out, int64_t ldo, const float* gamma, cudaStream_t st,
+                const GemmLnArgs* lnargs = nullptr);
 int launch_attention(vtq_ctx* ctx, const void* qkv, void* out, int n_seq, int S, int heads, int dtype,
                      int q_rows, cudaStream_t st, long long* trace = nullptr);
 

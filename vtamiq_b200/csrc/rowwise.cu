@@ -282,6 +282,32 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
+// Entry of the folded-LayerNorm chain (vtq_gemm_ln): fp32 rows -> RAW 16-bit copy + per-row (sum, sum of squares)
+// in statistics slot 0.  One warp per row.
+// ------------------------------------------------------------------------------------------------
+template <int DT, int VPL>
+__global__ void __launch_bounds__(256) rowstats_cast_kernel(const float* __restrict__ x, size_t rows,
+                                                            void* __restrict__ raw16, float2* __restrict__ stats) {
+  constexpr int HIDDEN = VPL * 128;
+  const size_t row = blockIdx.x * static_cast<size_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float4* src = reinterpret_cast<const float4*>(x + row * HIDDEN);
+  uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(raw16) + row * HIDDEN);
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const float4 v = src[lane + 32 * k];
+    s1 += (v.x + v.y) + (v.z + v.w);
+    s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s2))));
+    __stcg(dst + lane + 32 * k, make_uint2(pack2<DT>(v.x, v.y), pack2<DT>(v.z, v.w)));
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if (lane == 0) stats[row] = make_float2(s1, s2);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K7: diff[b] = gamma * (LN(x[b][token]) - LN(x[B+b][token])), fp32.  One warp per pair.
 // Only the quality-token rows need the encoder_norm; 1/sqrt (not rsqrt.approx) keeps this fp32-faithful.
 // ------------------------------------------------------------------------------------------------
@@ -452,6 +478,30 @@ extern "C" int vtq_layernorm(vtq_ctx* ctx, const float* x, int64_t x_stride, con
   }
   if (le != cudaSuccess) return check_cuda(ctx, le, "layernorm launch");
   VTQ_CHECK_LAUNCH(ctx, "layernorm launch");
+  return VTQ_OK;
+}
+
+extern "C" int vtq_rowstats_cast(vtq_ctx* ctx, const float* x, int64_t rows, int hidden, void* raw16_out,
+                                 float* ln_out, int dtype, void* stream) {
+  if (!ctx) return VTQ_ERR_INVALID;
+  VTQ_CHECK_ARG(ctx, x && raw16_out && ln_out, "null pointer");
+  VTQ_CHECK_ARG(ctx, hidden == 768 || hidden == 1024, "hidden must be 768 or 1024");
+  VTQ_CHECK_ARG(ctx, rows >= 1, "rows");
+  VTQ_CHECK_ARG(ctx, dtype == VTQ_F16 || dtype == VTQ_BF16, "dtype");
+  VTQ_CHECK_ARG(ctx, (reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(raw16_out) |
+                      reinterpret_cast<uintptr_t>(ln_out)) % 16 == 0, "pointers must be 16-byte aligned");
+  const unsigned blocks = static_cast<unsigned>((rows + 7) / 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t r = static_cast<size_t>(rows);
+  float2* stats = reinterpret_cast<float2*>(ln_out);
+  if (hidden == 768) {
+    if (dtype == VTQ_F16) rowstats_cast_kernel<DT_F16, 6><<<blocks, 256, 0, st>>>(x, r, raw16_out, stats);
+    else rowstats_cast_kernel<DT_BF16, 6><<<blocks, 256, 0, st>>>(x, r, raw16_out, stats);
+  } else {
+    if (dtype == VTQ_F16) rowstats_cast_kernel<DT_F16, 8><<<blocks, 256, 0, st>>>(x, r, raw16_out, stats);
+    else rowstats_cast_kernel<DT_BF16, 8><<<blocks, 256, 0, st>>>(x, r, raw16_out, stats);
+  }
+  VTQ_CHECK_LAUNCH(ctx, "rowstats_cast launch");
   return VTQ_OK;
 }
 

@@ -10,6 +10,7 @@ restates reference ``VTAMIQ.forward`` (modules/vtamiq/vtamiq.py:94-119) →
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import torch
@@ -45,6 +46,13 @@ class _LayerPack:
     w_fc2: torch.Tensor
     b_fc2: torch.Tensor
     g2: torch.Tensor | None
+    # LayerNorm folded into the consuming GEMM (vtq_gemm_ln): W' = W * ln_w, b' = b + W ln_b, colsum = sum_k W'
+    w_qkv_f: torch.Tensor
+    b_qkv_f: torch.Tensor
+    cs_qkv: torch.Tensor
+    w_fc1_f: torch.Tensor
+    b_fc1_f: torch.Tensor
+    cs_fc1: torch.Tensor
 
 
 class _Workspace:
@@ -66,6 +74,9 @@ class _Workspace:
         self.qkv = e(rows, 3 * H, dt=t16)
         self.att = e(rows, H, dt=t16)
         self.h1 = e(rows, Mlp, dt=t16)
+        # per-row (sum, sum of squares) partials handed from a residual GEMM to the GEMM behind the LayerNorm
+        self.ln_slots = max(int(_lib.load_library().vtq_gemm_ln_slots(H)), 1)
+        self.stats = e(self.ln_slots, rows, 2)
         self.diff = e((streams - 1) * B, H)
         self.q = e((streams - 1) * B)
         self.tail_ws = torch.empty(max(eng.ctx.workspace_bytes((streams - 1) * B, H), 16), dtype=torch.uint8,
@@ -79,7 +90,7 @@ class Engine:
     """Packed weights + workspaces + launch sequence for one VTAMIQ module on one device."""
 
     def __init__(self, model, operand_dtype: str = "fp16", use_cuda_graph: bool = True,
-                 prune_last_block: bool = True):
+                 prune_last_block: bool = True, fuse_layernorm: bool | None = None):
         if operand_dtype not in _DTYPES:
             raise ValueError(f"operand_dtype must be one of {list(_DTYPES)}")
         self.model = model
@@ -87,6 +98,12 @@ class Engine:
         self.vtq16, self.torch16 = _DTYPES[operand_dtype]
         self.use_cuda_graph = use_cuda_graph
         self.prune_last_block = prune_last_block   # last block: quality-token row only after K/V (exact)
+        # encoder LayerNorms carried by the GEMMs either side of them (needs >= 256 token rows).  Opt-in: measured
+        # 3-4 % SLOWER per step at cfg2 than the separate LayerNorm kernel.  When the caller does
+        # not choose, VTQ_FUSE_LN=1 turns it on (A/B runs).
+        if fuse_layernorm is None:
+            fuse_layernorm = os.environ.get("VTQ_FUSE_LN", "0") == "1"
+        self.fuse_layernorm = bool(fuse_layernorm)
         self.device = None
         self.ctx = None
         self._sig = None
@@ -166,9 +183,22 @@ class Engine:
         else:
             self.scale_table, self.num_scales = None, 0
         self.layers = []
+
+        def fold(w, b, ln_w, ln_b):
+            """LN(x) W^T + b == rstd (x W'^T - mean colsum) + b'  with the LayerNorm affine folded into W', b'."""
+            w32 = w.detach().float()
+            wf = (w32 * ln_w.detach().float()[None, :]).to(t16).contiguous()
+            bf = (b.detach().float() + w32 @ ln_b.detach().float()).contiguous()
+            return wf, bf, wf.float().sum(1).contiguous()
+
         for L in vit.encoder.layers:
             a = L.attn
+            w_qkv32 = torch.cat([a.query.weight, a.key.weight, a.value.weight], 0)
+            b_qkv32 = torch.cat([a.query.bias, a.key.bias, a.value.bias], 0)
+            w_qkv_f, b_qkv_f, cs_qkv = fold(w_qkv32, b_qkv32, L.attention_norm.weight, L.attention_norm.bias)
+            w_fc1_f, b_fc1_f, cs_fc1 = fold(L.ffn.fc1.weight, L.ffn.fc1.bias, L.ffn_norm.weight, L.ffn_norm.bias)
             self.layers.append(_LayerPack(
+                w_qkv_f=w_qkv_f, b_qkv_f=b_qkv_f, cs_qkv=cs_qkv, w_fc1_f=w_fc1_f, b_fc1_f=b_fc1_f, cs_fc1=cs_fc1,
                 ln1_w=f32(L.attention_norm.weight), ln1_b=f32(L.attention_norm.bias),
                 w_qkv=h16(torch.cat([a.query.weight, a.key.weight, a.value.weight], 0)),
                 b_qkv=f32(torch.cat([a.query.bias, a.key.bias, a.value.bias], 0)),
@@ -242,10 +272,21 @@ class Engine:
           _ptr(ws.pos_idx) if self.dump_indices else None, _ptr(ws.scale_idx) if self.dump_indices else None, st)
         eps = self.ln_eps
         n_layers = len(self.layers)
+        # Folded LayerNorms: ws.ln holds the RAW 16-bit copy of x, ws.stats each row's (sum, sum of squares) partials;
+        # the residual GEMMs (out-projection, fc2) refresh both, the GEMMs behind a LayerNorm (QKV, fc1) consume them.
+        fold = self.fuse_layernorm and rows >= 256
+        slots_in = 1
+        if fold:
+            c("rowstats_cast", "vtq_rowstats_cast", _ptr(ws.x), rows, H, _ptr(ws.ln), _ptr(ws.stats), dt, st)
         for li, L in enumerate(self.layers):
-            c("layernorm", "vtq_layernorm", _ptr(ws.x), 0, _ptr(L.ln1_w), _ptr(L.ln1_b), eps, rows, H, _ptr(ws.ln), dt, st)
-            c("gemm_qkv", "vtq_gemm", _ptr(ws.ln), 0, _ptr(L.w_qkv), _ptr(L.b_qkv), rows, 3 * H, H, dt, EPI_BIAS_H,
-              _ptr(ws.qkv), 0, None, st)
+            if fold:
+                c("gemm_qkv", "vtq_gemm_ln", _ptr(ws.ln), 0, _ptr(L.w_qkv_f), _ptr(L.b_qkv_f), rows, 3 * H, H, dt,
+                  EPI_BIAS_H, _ptr(ws.qkv), 0, None, _ptr(ws.stats), slots_in, _ptr(L.cs_qkv), eps, None, None, st)
+            else:
+                c("layernorm", "vtq_layernorm", _ptr(ws.x), 0, _ptr(L.ln1_w), _ptr(L.ln1_b), eps, rows, H, _ptr(ws.ln),
+                  dt, st)
+                c("gemm_qkv", "vtq_gemm", _ptr(ws.ln), 0, _ptr(L.w_qkv), _ptr(L.b_qkv), rows, 3 * H, H, dt, EPI_BIAS_H,
+                  _ptr(ws.qkv), 0, None, st)
             if self.prune_last_block and li == n_layers - 1:
                 # Only the quality token of each sequence survives the encoder (transformer.py:634, vtamiq.py:104-108):
                 # in the last block K/V still need every row, but attention output, out-projection, LayerNorm and the
@@ -265,6 +306,16 @@ class Engine:
                   EPI_BIAS_RESID_F32, x_tok, S * H, _ptr(L.g2), st)
                 continue
             c("attention", "vtq_attention_fwd", _ptr(ws.qkv), _ptr(ws.att), n_seq, S, self.heads, dt, 0, st)
+            if fold:
+                c("gemm_out", "vtq_gemm_ln", _ptr(ws.att), 0, _ptr(L.w_o), _ptr(L.b_o), rows, H, H, dt,
+                  EPI_BIAS_RESID_F32, _ptr(ws.x), 0, _ptr(L.g1), None, 0, None, 0.0, _ptr(ws.ln), _ptr(ws.stats), st)
+                slots_in = ws.ln_slots
+                c("gemm_fc1", "vtq_gemm_ln", _ptr(ws.ln), 0, _ptr(L.w_fc1_f), _ptr(L.b_fc1_f), rows, self.mlp_dim, H,
+                  dt, EPI_BIAS_GELU_H, _ptr(ws.h1), 0, None, _ptr(ws.stats), slots_in, _ptr(L.cs_fc1), eps, None,
+                  None, st)
+                c("gemm_fc2", "vtq_gemm_ln", _ptr(ws.h1), 0, _ptr(L.w_fc2), _ptr(L.b_fc2), rows, H, self.mlp_dim, dt,
+                  EPI_BIAS_RESID_F32, _ptr(ws.x), 0, _ptr(L.g2), None, 0, None, 0.0, _ptr(ws.ln), _ptr(ws.stats), st)
+                continue
             c("gemm_out", "vtq_gemm", _ptr(ws.att), 0, _ptr(L.w_o), _ptr(L.b_o), rows, H, H, dt, EPI_BIAS_RESID_F32,
               _ptr(ws.x), 0, _ptr(L.g1), st)
             c("layernorm", "vtq_layernorm", _ptr(ws.x), 0, _ptr(L.ln2_w), _ptr(L.ln2_b), eps, rows, H, _ptr(ws.ln), dt, st)
@@ -280,16 +331,12 @@ class Engine:
         c("diffnet_head", "vtq_diffnet_head", _ptr(ws.diff), self._tail_params, len(self._tail_params), self.num_rgs,
           self.num_rcabs, H, self.ca_hidden, self.head_hidden, nq, _ptr(ws.q), _ptr(ws.tail_ws), st)
 
-    def launches_per_forward(self, embedded: bool = False) -> int:
-        """Kernels of ours in one encode+score pass (excludes the input staging kernels)."""
-        return (0 if embedded else 1) + 1 + 7 * len(self.layers) + 2   # + cls_diff + fused DiffNet/head
-
     def run(self, ws: _Workspace, embedded: bool = False):
         """Encode + score the staged inputs; uses a captured CUDA graph per workspace when enabled."""
         if not self.use_cuda_graph or self.dump_indices or self.timeline is not None:
             self._encode_and_score(ws, embedded)
             return
-        key = ("emb" if embedded else "patch", self.prune_last_block)
+        key = ("emb" if embedded else "patch", self.prune_last_block, self.fuse_layernorm)
         if ws.graph is None or ws.graph[0] != key:
             # warm-up outside capture (cudaFuncSetAttribute, lazy module load), then capture
             self._encode_and_score(ws, embedded)

@@ -73,11 +73,14 @@ class VTAMIQ(VisionTransformerBackbone):
       prune_last_block  evaluate the last encoder block's attention output / projection / MLP only for the quality
                      token row of each sequence (its K/V still see every row) — the rows the reference discards at
                      transformer.py:634; identical scores, ~6 % less work.
+      fuse_layernorm  (default off) carry the encoder's LayerNorms inside the GEMMs either side of them
+                     (vtq_gemm_ln) instead of separate passes over the fp32 residual stream; same scores within
+                     5e-4, but measured slower at the benchmark configuration — kept as an option.
     """
 
     def __init__(self, vit_config=None, calibrate=True, diff_scale=True, num_rgs=4, num_rcabs=4, rg_path_drop=0.1,
                  ca_reduction=8, predictor_dropout=0., return_features=False, operand_dtype="fp16",
-                 cuda_graph=True, prune_last_block=True, **kwargs):
+                 cuda_graph=True, prune_last_block=True, fuse_layernorm=None, **kwargs):
         vit_config = dict(vit_config) if vit_config is not None else {}
         _warn_unused("VTAMIQ", kwargs)
         vit_config.pop("use_classifier", None)
@@ -98,7 +101,8 @@ class VTAMIQ(VisionTransformerBackbone):
         self.return_features = return_features
         # not a Module / Parameter: invisible to state_dict()
         object.__setattr__(self, "_engine", Engine(self, operand_dtype=operand_dtype, use_cuda_graph=cuda_graph,
-                                                   prune_last_block=prune_last_block))
+                                                   prune_last_block=prune_last_block,
+                                                   fuse_layernorm=fuse_layernorm))
 
     # -- reference API ---------------------------------------------------------------------------
     def set_freeze_state(self, freeze_state, freeze_dict):
