@@ -7,15 +7,19 @@
 //   warp 0      TMA producer : both Q tiles once, then K/V tiles (128 keys x 64) through a 3-deep smem ring that
 //                              the two query tiles share
 //   warp 1      MMA issuer   : S_t = Q_t K^T (tcgen05.mma M128 N128 K16 x4, both operands K-major) and
-//                              O_t += P_t V (M128 N64 K16 x8, A = P from smem, B = V as an MN-major operand — V is
-//                              consumed exactly as the QKV GEMM wrote it, no transpose pass), for t = A, B
+//                              O_t += P_t V (M128 N64 K16 x8, A = P_t read straight from TENSOR MEMORY, B = V as an
+//                              MN-major smem operand — V is consumed exactly as the QKV GEMM wrote it, no transpose
+//                              pass), for t = A, B
 //   warps 4..7  softmax A    : one query row per thread.  The whole 128-key score row is pulled from TMEM into
 //   warps 8..11 softmax B      registers ONCE and the S buffer is released immediately, so Q_t K^T of the next key
 //                              tile runs underneath this tile's exponentials; running max / sum in fp32, lazy
 //                              rescaling (O is only corrected when the max grows by > 2^8), P rounded to 16 bits
-//                              into 128B-swizzled smem, final O / l through per-warp TMA stores.
+//                              and written back to TMEM with tcgen05.st (row = lane, two keys per column: the
+//                              K-major A layout of tcgen05.mma), so P never touches shared memory; final O / l
+//                              through per-warp TMA stores.
 // Registers are re-partitioned with setmaxnreg: the producer warpgroup drops to 56, the softmax warpgroups grow to
-// 224 (56*128 + 224*256 = 168*384, the launch allocation) so a whole score row (128 fp32) fits.  TMEM (512 columns): S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384).
+// 224 (56*128 + 224*256 = 168*384, the launch allocation) so a whole score row (128 fp32) fits.
+// TMEM (512 columns): S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512).
 // Replaces modules/VisionTransformer/transformer.py:158-166 (matmul, /sqrt(d), softmax, matmul, permute copy).
 #include <cstdlib>
 
@@ -30,13 +34,14 @@ constexpr int ATT_D = 64;
 constexpr int ATT_THREADS = 3 * 128;  // warpgroup 0: TMA + MMA warps (+2 idle), warpgroups 1, 2: softmax A, B
 constexpr int ATT_TILE_BYTES = 128 * ATT_D * 2;  // 16 KB: a 128-row x 64 x 16-bit tile
 constexpr int ATT_KV_STAGES = 3;
-constexpr int ATT_P_BYTES = ATT_BQ * ATT_BKV * 2;  // 32 KB per query tile
-constexpr int ATT_SMEM_BYTES = ATT_TILE_BYTES * (4 + 2 * ATT_KV_STAGES) + 2 * ATT_P_BYTES + 256;
+constexpr int ATT_OUT_BYTES = ATT_BQ * ATT_D * 2;  // 16 KB output staging per query tile (4 warps x 32 rows x 128 B)
+constexpr int ATT_SMEM_BYTES = ATT_TILE_BYTES * (4 + 2 * ATT_KV_STAGES) + 2 * ATT_OUT_BYTES + 256;
 static_assert(ATT_SMEM_BYTES <= 227 * 1024, "smem budget");
 constexpr int ATT_XU_RELEASE_CHUNK = 11;  // of 16 eight-key chunks per row
 constexpr uint32_t ATT_TMEM_COLS = 512;
 constexpr uint32_t ATT_TMEM_S = 0;    // + t * 128
 constexpr uint32_t ATT_TMEM_O = 256;  // + t * 64
+constexpr uint32_t ATT_TMEM_P = 384;  // + t * 64: P_t as the K-major A operand of P V (two 16-bit keys per column)
 
 // Diagnostics (vtq_attention_fwd_trace): CTA 0 records clock64() at pipeline events; slot layout
 // trace[role * 512 + event_index], role 0 = MMA thread, 1 = softmax A (warp 4 lane 0), 2 = softmax B.
@@ -54,8 +59,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
   uint8_t* sQ = smem;                                  // [2 buffers][2 tiles]
   uint8_t* sK = sQ + 4 * ATT_TILE_BYTES;               // [stages]
   uint8_t* sV = sK + ATT_KV_STAGES * ATT_TILE_BYTES;   // [stages]
-  uint8_t* sP = sV + ATT_KV_STAGES * ATT_TILE_BYTES;   // [2 tiles]; also the output staging of each work item
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * ATT_P_BYTES);
+  uint8_t* sO = sV + ATT_KV_STAGES * ATT_TILE_BYTES;   // [2 tiles] output staging of each work item
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sO + 2 * ATT_OUT_BYTES);
   uint64_t* q_full = bars;            // [2] Q pair of a work item landed            (TMA tx)
   uint64_t* q_empty = bars + 2;       // [2] all Q K^T of that work item retired     (MMA commit)
   uint64_t* kv_full = bars + 4;       // [3]
@@ -158,17 +163,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
           ATT_TRACE(0, tr++);
         };
         auto issue_pv = [&](int t, uint32_t kv_idx, bool first) {
-          // O_t (+)= P_t V: 8 k-steps of 16 keys.  P: two 64-key K-major blocks of 16 KB.  V: rows = keys, 128 B
+          // O_t (+)= P_t V: 8 k-steps of 16 keys.  P: tensor memory, 8 columns per k-step.  V: rows = keys, 128 B
           // apart, 8-key groups 1024 B apart -> one k-step advances the start address by 2048 B.
           mbar_wait(&p_full[t], n_p[t] & 1);
           tc_fence_after();
-          const uint32_t aP = smem_u32(sP + t * ATT_P_BYTES);
           const uint32_t aV = smem_u32(sV + (kv_idx % ATT_KV_STAGES) * ATT_TILE_BYTES);
 #pragma unroll
           for (int kk = 0; kk < ATT_BKV / 16; ++kk) {
-            const uint64_t dP = umma_smem_desc(aP + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
             const uint64_t dV = umma_smem_desc(aV + kk * 2048, 1024, 1024);
-            umma_f16_ss(tmem_base + ATT_TMEM_O + t * 64, dP, dV, idesc_pv, (!first || kk) ? 1u : 0u);
+            umma_f16_ts(tmem_base + ATT_TMEM_O + t * 64, tmem_base + ATT_TMEM_P + t * 64 + kk * 8, dV, idesc_pv,
+                        (!first || kk) ? 1u : 0u);
           }
           umma_commit(&pv_done[t]);
           ++n_p[t];
@@ -212,13 +216,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
     // ------------------------------- softmax / correction / output --------------
     const int t = (warp - 4) >> 2;         // query tile of this warpgroup
     const int lane_grp = warp & 3;         // TMEM lane quarter of this warp
-    const int row = lane_grp * 32 + lane;  // query row inside the tile == TMEM lane
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16);
     const uint32_t tS = t_lane + ATT_TMEM_S + t * 128;
     const uint32_t tO = t_lane + ATT_TMEM_O + t * 64;
-    const uint32_t swz = static_cast<uint32_t>(row & 7);
-    const uint32_t p_row = smem_u32(sP + t * ATT_P_BYTES) + row * 128;
-    uint8_t* stage_out = sP + t * ATT_P_BYTES + lane_grp * 4096;  // == this warp's 32 rows of P block 0
+    const uint32_t tP = t_lane + ATT_TMEM_P + t * 64;
+    uint8_t* stage_out = sO + t * ATT_OUT_BYTES + lane_grp * 4096;  // this warp's 32 output rows
     const uint32_t o_row = smem_u32(stage_out) + lane * 128;
     const uint32_t oswz = static_cast<uint32_t>(lane & 7);
     const float c = 0.125f * 1.44269504088896340736f;  // (1/sqrt(64)) * log2(e)
@@ -232,10 +234,6 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
       const int head = (w / nqp) % heads;
       const int seq = w / (nqp * heads);
       const int q0 = qp * (2 * ATT_BQ);
-      // the previous work item's output store must have finished reading the staging rows (they alias P_t)
-      if (lane == 0) tma_wait_group_read<0>();
-      __syncwarp();
-
       float m = -INFINITY;  // reference max (raw score domain) that P and O are currently scaled by
       float l = 0.f;        // running sum of exp
       bool s_ok = false;    // early probe of the next S tile (issued before the exponentials of the current one)
@@ -312,11 +310,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         if (!turn_ok) mbar_wait(&xu_turn[t], turn_parity);
         if (tracer) ATT_TRACE(1 + t, tr++);  // 5: SFU turn acquired
         s_ok = (j + 1 < nkv) && mbar_test(&s_full[t], (n + 1) & 1);  // consumed at the top of the next tile
-        // p = exp2(s*c - m*c): packed FFMA2 + MUFU.EX2, packed partial sums, 16-bit P into swizzled smem
+        // p = exp2(s*c - m*c): packed FFMA2 + MUFU.EX2, packed partial sums, 16-bit P into tensor memory
         f32x2 sum_a = 0ull, sum_b = 0ull;
+        uint32_t pq[8];  // 16 keys of P, packed; stored to TMEM as one 8-column piece (= one k-step of P V)
 #pragma unroll
-        for (int cc = 0; cc < ATT_BKV / 8; ++cc) {  // 8 keys = one 16-byte chunk of this row
-          uint32_t pk[4];
+        for (int cc = 0; cc < ATT_BKV / 8; ++cc) {  // 8 keys per step
 #pragma unroll
           for (int q = 0; q < 4; q += 2) {
             const int e = cc * 8 + q * 2;
@@ -326,11 +324,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
             const float p0 = ex2_approx(t0), p1 = ex2_approx(t1), p2 = ex2_approx(t2), p3 = ex2_approx(t3);
             sum_a = f2_add(sum_a, f2_pack(p0, p1));
             sum_b = f2_add(sum_b, f2_pack(p2, p3));
-            pk[q] = pack2<DT>(p0, p1);
-            pk[q + 1] = pack2<DT>(p2, p3);
+            pq[(cc & 1) * 4 + q] = pack2<DT>(p0, p1);
+            pq[(cc & 1) * 4 + q + 1] = pack2<DT>(p2, p3);
           }
-          const uint32_t blk = p_row + (cc >> 3) * 16384;  // 64-key K-major block
-          st_shared_v4(blk + ((static_cast<uint32_t>(cc & 7) ^ swz) << 4), pk[0], pk[1], pk[2], pk[3]);
+          if (cc & 1) tmem_st8(tP + (cc >> 1) * 8, pq);
           if (cc == ATT_XU_RELEASE_CHUNK) {
             // hand the SFU to the other group about one barrier wake-up latency before this group's last
             // exponentials issue
@@ -343,13 +340,15 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
           f2_unpack(f2_add(sum_a, sum_b), s0, s1);
           l += s0 + s1;
         }
-        fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        tmem_wait_st();  // P_t is in tensor memory
         tc_fence_before();
         mbar_arrive(&p_full[t]);
         if (tracer) ATT_TRACE(1 + t, tr++);  // 6: P published
       }
 
-      // output: O / l -> 16 bit -> staging (P_t is free once the last P V retired) -> TMA store
+      // output: O / l -> 16 bit -> this warp's staging rows -> TMA store
+      if (lane == 0) tma_wait_group_read<0>();  // the previous work item's store has finished reading them
+      __syncwarp();
       mbar_wait(&pv_done[t], (n - 1) & 1);
       tc_fence_after();
       uint32_t o0[32], o1[32];
