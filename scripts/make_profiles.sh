@@ -14,3 +14,4 @@ python scripts/gemm_traffic.py gpurun_out/prof_gemm2.ncu-rep profiles/gemm_traff
 tail -3 gpurun_out/pytest_gpu.log > profiles/${R}_pytest_gpu.txt
 tail -2 gpurun_out/smoke.log > profiles/${R}_smoke.txt
 cat gpurun_out/host.txt > profiles/${R}_host.txt
+python scripts/make_summary.py ${R} > /dev/null

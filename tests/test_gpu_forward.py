@@ -202,9 +202,10 @@ def test_last_block_pruning_is_exact():
 
 
 @pytest.mark.parametrize("prune", [True, False])
-def test_layernorm_folding_matches_separate_layernorm(prune):
-    """LayerNorms carried by the GEMMs (vtq_gemm_ln) vs the separate LayerNorm kernel: same scores up to the
-    16-bit rounding point moving from LN(x) to x, far inside the parity bar."""
+def test_layernorm_folding_matches_oracle_and_separate_layernorm(prune):
+    """LayerNorms carried by the GEMMs (vtq_gemm_ln) instead of the separate LayerNorm kernel: the 16-bit rounding
+    point moves from LN(x) to x, so the two paths are two roundings of the same fp32 math — both inside the
+    parity bar against the oracle, and close to each other."""
     B, N = 4, 300
     g = torch.Generator(device="cuda").manual_seed(7)
     p = (torch.randn(B, N, 3, 16, 16, device="cuda", generator=g), torch.randn(B, N, 3, 16, 16, device="cuda", generator=g))
@@ -217,8 +218,12 @@ def test_layernorm_folding_matches_separate_layernorm(prune):
         qa, _ = a(p, pos, (None, None))
         qb, _ = b(p, pos, (None, None))
         qa2, _ = a(p, pos, (None, None))
+    sd = {k: v.detach().cpu() for k, v in a.state_dict().items()}
+    want = vtamiq_oracle.vtamiq_forward(sd, tuple(t.cpu() for t in p), tuple(t.cpu() for t in pos), None)
     assert torch.equal(qa, qa2)                      # fixed statistics slots: deterministic
-    assert (qa - qb).abs().max().item() < 5e-4, (qa, qb)
+    assert (qa.cpu() - want).abs().max().item() <= SCORE_TOL, (qa, want)
+    assert (qb.cpu() - want).abs().max().item() <= SCORE_TOL, (qb, want)
+    assert (qa - qb).abs().max().item() < 1.5e-3, (qa, qb)
 
 
 def _pairs(B, H, W, counts, seed):
