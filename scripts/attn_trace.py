@@ -37,3 +37,27 @@ for role in (1, 2):
             print(f"  item {item} output: {int(r[i] - r[i-1])} cycles")
             i += 1
         item += 1
+
+if os.environ.get("ATT_TIMELINE"):   # ATT_TIMELINE=1 [ATT_LO=.. ATT_HI=..]: merged event list of CTA 0
+    # merged timeline of one work item (the second): MMA issues vs softmax phases
+    ev = []
+    m = t[0][t[0] > 0] - t0
+    # MMA stamps per item at S=501: 2 (first QK A,B) + 4 tiles * (up to 4) ... just label sequentially
+    for i, x in enumerate(m): ev.append((int(x), f"MMA issue #{i}"))
+    names = ["start(wait S)", "S ready", "S in regs", "max done", "PV retired", "turn acquired", "P published"]
+    for role in (1, 2):
+        r = t[role][t[role] > 0] - t0
+        i = 0; item = 0
+        while i < len(r):
+            for j in range(4):
+                for k in range(7):
+                    if i < len(r): ev.append((int(r[i]), f"{'AB'[role-1]} item{item} tile{j} {names[k]}")); i += 1
+            if i < len(r): ev.append((int(r[i]), f"{'AB'[role-1]} item{item} output issued")); i += 1
+            item += 1
+    ev.sort()
+    lo, hi = int(os.environ.get("ATT_LO", 18000)), int(os.environ.get("ATT_HI", 36000))
+    prev = None
+    for x, s in ev:
+        if lo <= x <= hi:
+            print(f"{x:8d} (+{0 if prev is None else x - prev:5d}) {s}")
+            prev = x
