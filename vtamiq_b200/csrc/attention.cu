@@ -179,34 +179,55 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
           ATT_TRACE(0, tr++);
         };
 
-        uint32_t it = 0, kvc = 0;
-        for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
-          const uint32_t qb = it & 1;
-          mbar_wait(&q_full[qb], (it >> 1) & 1);
-          mbar_wait(&kv_full[kvc % ATT_KV_STAGES], (kvc / ATT_KV_STAGES) & 1);
+        // One flat walk over this CTA's key tiles, ACROSS work items: g = global key-tile index (= K/V ring
+        // counter), Q K^T always runs one tile ahead of P V — also over a work-item boundary, so the first score
+        // tile of the next item is computed underneath the last exponentials / the output of the current one.
+        const uint32_t my_items = static_cast<uint32_t>((n_items - static_cast<int>(blockIdx.x) + gridDim.x - 1) / gridDim.x);
+        const uint32_t total = my_items * static_cast<uint32_t>(nkv);
+        uint32_t qk_it = 0, qk_j = 0;  // (work item, key tile) of the next Q K^T pair to issue
+        auto issue_qk_pair = [&](uint32_t g) {
+          const uint32_t qb = qk_it & 1;
+          if (qk_j == 0) mbar_wait(&q_full[qb], (qk_it >> 1) & 1);
+          mbar_wait(&kv_full[g % ATT_KV_STAGES], (g / ATT_KV_STAGES) & 1);
           tc_fence_after();
-          issue_qk(0, qb, kvc);
-          issue_qk(1, qb, kvc);
-          for (int j = 0; j < nkv; ++j) {
-            const bool more = j + 1 < nkv;
-            const uint32_t kn = kvc + j + 1;
-            if (more) {
-              mbar_wait(&kv_full[kn % ATT_KV_STAGES], (kn / ATT_KV_STAGES) & 1);
+          issue_qk(0, qb, g);
+          issue_qk(1, qb, g);
+          if (++qk_j == static_cast<uint32_t>(nkv)) {
+            umma_commit(&q_empty[qb]);  // every Q K^T of this work item has been issued
+            qk_j = 0;
+            ++qk_it;
+          }
+        };
+        issue_qk_pair(0);
+        uint32_t it = 0, j = 0;  // (work item, key tile) of the P V being issued
+        for (uint32_t g = 0; g < total; ++g) {
+          const bool more = g + 1 < total;
+          if (more) {
+            // both query tiles' next score tiles first: S_t(g) was pulled into registers long ago
+            const uint32_t qb = qk_it & 1;
+            if (qk_j == 0) mbar_wait(&q_full[qb], (qk_it >> 1) & 1);
+            mbar_wait(&kv_full[(g + 1) % ATT_KV_STAGES], ((g + 1) / ATT_KV_STAGES) & 1);
+            tc_fence_after();
+          }
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            if (more) issue_qk(t, qk_it & 1, g + 1);  // next score tile runs underneath this tile's exponentials
+            if (j == 0 && it > 0) {                   // the first P V of a work item overwrites O_t: previous O read out?
+              mbar_wait(&o_free[t], (it - 1) & 1);
               tc_fence_after();
             }
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-              if (more) issue_qk(t, qb, kn);  // next score tile runs underneath this tile's exponentials
-              if (j == 0 && it > 0) {         // the first P V of a work item overwrites O_t: previous O read out?
-                mbar_wait(&o_free[t], (it - 1) & 1);
-                tc_fence_after();
-              }
-              issue_pv(t, kvc + j, j == 0);
-            }
-            if (!more) umma_commit(&q_empty[qb]);            // every Q K^T of this work item has been issued
-            umma_commit(&kv_empty[(kvc + j) % ATT_KV_STAGES]);  // K(j), V(j) free once everything above retires
+            issue_pv(t, g, j == 0);
           }
-          kvc += nkv;
+          if (more && ++qk_j == static_cast<uint32_t>(nkv)) {
+            umma_commit(&q_empty[qk_it & 1]);  // every Q K^T of that work item has been issued
+            qk_j = 0;
+            ++qk_it;
+          }
+          umma_commit(&kv_empty[g % ATT_KV_STAGES]);  // K(g), V(g) free once everything above retires
+          if (++j == static_cast<uint32_t>(nkv)) {
+            j = 0;
+            ++it;
+          }
         }
       }
       __syncwarp();
