@@ -85,11 +85,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
     tma_prefetch_desc(&tmO);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&q_full[b], 1);
-      mbar_init(&q_empty[b], 1);
+      mbar_init(&q_empty[b], 2);
     }
     for (int s = 0; s < ATT_KV_STAGES; ++s) {
       mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
+      mbar_init(&kv_empty[s], 2);
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
@@ -138,9 +138,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         }
       }
       __syncwarp();
-    } else if (warp == 1) {
-      // ------------------------------- MMA issuer ---------------------------------
+    } else if (warp <= 2) {
+      // ------------------------------- MMA issuers: warp 1 -> query tile A, warp 2 -> query tile B ------------
       if (lane == 0) {
+        const int mt = warp - 1;
         constexpr uint32_t idesc_qk = umma_idesc_f16(DT, ATT_BQ, ATT_BKV, 0, 0);
         constexpr uint32_t idesc_pv = umma_idesc_f16(DT, ATT_BQ, ATT_D, 0, 1);  // B (=V) is MN-major
         uint32_t n_s[2] = {0, 0};  // score tiles issued per query tile (global over work items)
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
                         k ? 1u : 0u);
           umma_commit(&s_full[t]);
           ++n_s[t];
-          ATT_TRACE(0, tr++);
+          if (mt == 0) ATT_TRACE(0, tr++);
         };
         auto issue_pv = [&](int t, uint32_t kv_idx, bool first) {
           // O_t (+)= P_t V: 8 k-steps of 16 keys.  P: tensor memory, 8 columns per k-step.  V: rows = keys, 128 B
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
           }
           umma_commit(&pv_done[t]);
           ++n_p[t];
-          ATT_TRACE(0, tr++);
+          if (mt == 0) ATT_TRACE(0, tr++);
         };
 
         // One flat walk over this CTA's key tiles, ACROSS work items: g = global key-tile index (= K/V ring
@@ -190,8 +191,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
           if (qk_j == 0) mbar_wait(&q_full[qb], (qk_it >> 1) & 1);
           mbar_wait(&kv_full[g % ATT_KV_STAGES], (g / ATT_KV_STAGES) & 1);
           tc_fence_after();
-          issue_qk(0, qb, g);
-          issue_qk(1, qb, g);
+          issue_qk(mt, qb, g);
           if (++qk_j == static_cast<uint32_t>(nkv)) {
             umma_commit(&q_empty[qb]);  // every Q K^T of this work item has been issued
             qk_j = 0;
@@ -203,27 +203,23 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         for (uint32_t g = 0; g < total; ++g) {
           const bool more = g + 1 < total;
           if (more) {
-            // both query tiles' next score tiles first: S_t(g) was pulled into registers long ago
             const uint32_t qb = qk_it & 1;
             if (qk_j == 0) mbar_wait(&q_full[qb], (qk_it >> 1) & 1);
             mbar_wait(&kv_full[(g + 1) % ATT_KV_STAGES], ((g + 1) / ATT_KV_STAGES) & 1);
             tc_fence_after();
+            issue_qk(mt, qk_it & 1, g + 1);  // next score tile runs underneath this tile's exponentials
           }
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            if (more) issue_qk(t, qk_it & 1, g + 1);  // next score tile runs underneath this tile's exponentials
-            if (j == 0 && it > 0) {                   // the first P V of a work item overwrites O_t: previous O read out?
-              mbar_wait(&o_free[t], (it - 1) & 1);
-              tc_fence_after();
-            }
-            issue_pv(t, g, j == 0);
+          if (j == 0 && it > 0) {            // the first P V of a work item overwrites O_t: previous O read out?
+            mbar_wait(&o_free[mt], (it - 1) & 1);
+            tc_fence_after();
           }
+          issue_pv(mt, g, j == 0);
           if (more && ++qk_j == static_cast<uint32_t>(nkv)) {
-            umma_commit(&q_empty[qk_it & 1]);  // every Q K^T of that work item has been issued
+            umma_commit(&q_empty[qk_it & 1]);  // every Q K^T of that work item (this tile) has been issued
             qk_j = 0;
             ++qk_it;
           }
-          umma_commit(&kv_empty[g % ATT_KV_STAGES]);  // K(g), V(g) free once everything above retires
+          umma_commit(&kv_empty[g % ATT_KV_STAGES]);  // K(g), V(g) free once both issuers' MMAs on them retire
           if (++j == static_cast<uint32_t>(nkv)) {
             j = 0;
             ++it;
