@@ -6,10 +6,14 @@
 // the tail of the current one.  The S x S score matrix lives only in TMEM / registers:
 //   warp 0      TMA producer : both Q tiles once, then K/V tiles (128 keys x 64) through a 3-deep smem ring that
 //                              the two query tiles share
-//   warp 1      MMA issuer   : S_t = Q_t K^T (tcgen05.mma M128 N128 K16 x4, both operands K-major) and
+//   warp 1, 2   MMA issuers  : one thread per query tile (t = A, B): the MMAs of a tile form a dependent chain
+//                              (each accumulates into the previous one's tile, ~125 cycles per instruction at these
+//                              sizes), so a single in-order issuer serialised both tiles' chains; S_t = Q_t K^T is
+//                              issued one key tile AHEAD, also across work-item boundaries.
+//                              S_t = Q_t K^T (tcgen05.mma M128 N128 K16 x4, both operands K-major) and
 //                              O_t += P_t V (M128 N64 K16 x8, A = P_t read straight from TENSOR MEMORY, B = V as an
 //                              MN-major smem operand — V is consumed exactly as the QKV GEMM wrote it, no transpose
-//                              pass), for t = A, B
+//                              pass)
 //   warps 4..7  softmax A    : one query row per thread.  The whole 128-key score row is pulled from TMEM into
 //   warps 8..11 softmax B      registers ONCE and the S buffer is released immediately, so Q_t K^T of the next key
 //                              tile runs underneath this tile's exponentials; running max / sum in fp32, lazy
