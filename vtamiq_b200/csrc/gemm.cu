@@ -719,10 +719,17 @@ static int launch_2cta(vtq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& 
   return VTQ_OK;
 }
 
-int gemm_ln_slots(int N) {
-  const int BN = (N % 256 == 0 && N >= 1536) ? 256 : (N % 192 == 0 ? 192 : 128);  // CTA-pair tile width, as below
-  return 2 * ((N + BN - 1) / BN);
+// Tile width of the CTA-pair kernel.  256 for the wide projections (QKV, fc1); N = 768 (attn.out, fc2, patch embed)
+// splits into 4 x 192 (504 pair-tiles on 74 pairs = 97 % wave efficiency; 3 x 256 gives 85 % and measures the same).
+// 128 only when nothing wider divides N: the MMAs of a tile form a dependent accumulation chain that advances at
+// ~125 cycles per instruction, and a 256 x 128 x 16 instruction is only 64 cycles of tensor work (measured at N = 768:
+// fc2 0.184 ms with BN = 128 vs 0.138 ms with 192 / 256).
+static int pick_bn_pair(int N) {
+  if (N % 256 == 0 && (N >= 1536 || N % 192 != 0)) return 256;
+  return (N % 192 == 0) ? 192 : 128;
 }
+
+int gemm_ln_slots(int N) { return 2 * ((N + pick_bn_pair(N) - 1) / pick_bn_pair(N)); }
 
 int launch_gemm(vtq_ctx* ctx, const void* A, int64_t lda, const void* W, const float* bias, int M, int N, int K,
                 int dtype, int epilogue, void* out, int64_t ldo, const float* gamma, cudaStream_t st,
@@ -780,10 +787,8 @@ int launch_gemm(vtq_ctx* ctx, const void* A, int64_t lda, const void* W, const f
       ln_mode = LN_PRODUCE;
     }
   }
-  // Tile width: 256 for the wide projections (QKV, fc1); N = 768 (attn.out, fc2, patch embed) splits into
-  // 4 x 192 under the CTA-pair kernel (504 pair-tiles on 74 pairs = 97 % wave efficiency; 3 x 256 gives 85 %).
   int BN;
-  if (two_cta) BN = (N % 256 == 0 && N >= 1536) ? 256 : (N % 192 == 0 ? 192 : 128);
+  if (two_cta) BN = pick_bn_pair(N);
   else BN = (N % 256 == 0 && N >= 1536) ? 256 : 128;
 
   CUtensorMap tmA, tmB, tmO;
