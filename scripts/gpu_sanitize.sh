@@ -18,3 +18,5 @@ print("q", q.cpu().numpy())
 PY
 timeout 900 compute-sanitizer --tool memcheck --launch-timeout 600 --print-limit 20 python /tmp/san.py > gpurun_out/sanitizer_memcheck.log 2>&1
 echo "memcheck rc=$?"; grep -E "ERROR SUMMARY|Invalid|q \[" gpurun_out/sanitizer_memcheck.log | head
+VTQ_FUSE_LN=1 timeout 900 compute-sanitizer --tool memcheck --launch-timeout 600 --print-limit 20 python /tmp/san.py > gpurun_out/sanitizer_memcheck_fuse_ln.log 2>&1
+echo "memcheck (LayerNorm folding) rc=$?"; grep -E "ERROR SUMMARY|Invalid|q \[" gpurun_out/sanitizer_memcheck_fuse_ln.log | head
