@@ -196,3 +196,29 @@ def test_gelu_polynomial_accuracy():
     # relative to fp16 resolution of the stored activation: well inside half an ulp wherever |gelu| >= 1e-2
     big = np.abs(want) >= 1e-2
     assert (np.abs(got - want)[big] / np.abs(want)[big]).max() < 2.5e-4
+
+
+def test_layernorm_folding_algebra():
+    """Engine.fold_layernorm: LN(x) W^T + b == rstd (x W'^T - mean colsum) + b' (what vtq_gemm_ln's epilogue applies),
+    checked in fp64 on the fp16-rounded W' so that only the algebra is under test."""
+    import torch
+    from vtamiq_b200.engine import fold_layernorm
+    g = torch.Generator().manual_seed(0)
+    K, N, M, eps = 96, 40, 17, 1e-6
+    x = torch.randn(M, K, generator=g, dtype=torch.float64) * 2 + 0.3
+    w = torch.randn(N, K, generator=g) * 0.1
+    b = torch.randn(N, generator=g)
+    ln_w = torch.rand(K, generator=g) + 0.5
+    ln_b = torch.randn(K, generator=g) * 0.2
+    wf, bf, cs = fold_layernorm(w, b, ln_w, ln_b, torch.float16)
+    assert wf.dtype == torch.float16 and bf.dtype == torch.float32 and cs.shape == (N,)
+    mean = x.mean(1, keepdim=True)
+    rstd = 1.0 / torch.sqrt(x.var(1, unbiased=False, keepdim=True) + eps)
+    folded = rstd * (x @ wf.double().t() - mean * cs.double()[None, :]) + bf.double()[None, :]
+    # same math with the LayerNorm applied explicitly, on the same rounded W' (divide the LN weight back out)
+    ln = (x - mean) * rstd
+    want = ln @ wf.double().t() + (b.double() + w.double() @ ln_b.double())[None, :]
+    assert (folded - want).abs().max().item() < 1e-5
+    # and against the textbook form with unrounded weights: only the fp16 rounding of W' apart
+    ref = torch.nn.functional.layer_norm(x, (K,), ln_w.double(), ln_b.double(), eps) @ w.double().t() + b.double()
+    assert (folded - ref).abs().max().item() < 2e-2

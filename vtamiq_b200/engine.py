@@ -55,6 +55,19 @@ class _LayerPack:
     cs_fc1: torch.Tensor
 
 
+def fold_layernorm(w, b, ln_w, ln_b, dtype16):
+    """Operands of vtq_gemm_ln's consumer side for ``Linear(LayerNorm(x))``.
+
+    LN(x) W^T + b == rstd * (x W'^T - mean * colsum) + b'   with   W' = W * ln_w (rounded to the 16-bit operand type),
+    b' = b + W ln_b,  colsum = sum_k W'[n, k] (of the ROUNDED W', the matrix the tensor core actually multiplies).
+    Returns (W' 16-bit, b' fp32, colsum fp32).
+    """
+    w32 = w.detach().float()
+    wf = (w32 * ln_w.detach().float()[None, :]).to(dtype16).contiguous()
+    bf = (b.detach().float() + w32 @ ln_b.detach().float()).contiguous()
+    return wf, bf, wf.float().sum(1).contiguous()
+
+
 class _Workspace:
     """Device buffers for one (B, N) problem; allocated once, reused by every forward / graph replay."""
 
@@ -184,12 +197,7 @@ class Engine:
             self.scale_table, self.num_scales = None, 0
         self.layers = []
 
-        def fold(w, b, ln_w, ln_b):
-            """LN(x) W^T + b == rstd (x W'^T - mean colsum) + b'  with the LayerNorm affine folded into W', b'."""
-            w32 = w.detach().float()
-            wf = (w32 * ln_w.detach().float()[None, :]).to(t16).contiguous()
-            bf = (b.detach().float() + w32 @ ln_b.detach().float()).contiguous()
-            return wf, bf, wf.float().sum(1).contiguous()
+        fold = lambda w, b, ln_w, ln_b: fold_layernorm(w, b, ln_w, ln_b, t16)
 
         for L in vit.encoder.layers:
             a = L.attn
