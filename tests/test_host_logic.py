@@ -222,3 +222,19 @@ def test_layernorm_folding_algebra():
     # and against the textbook form with unrounded weights: only the fp16 rounding of W' apart
     ref = torch.nn.functional.layer_norm(x, (K,), ln_w.double(), ln_b.double(), eps) @ w.double().t() + b.double()
     assert (folded - ref).abs().max().item() < 2e-2
+
+
+def test_empty_batch_and_shape_errors_need_no_device():
+    """Edge cases handled on the host before any kernel is involved: B = 0 returns an empty score vector like the
+    reference; mismatched ref/dist shapes and N = 0 raise."""
+    import pytest
+    import torch
+    import vtamiq_b200
+    m = vtamiq_b200.VTAMIQ(vit_config=dict(pretrained=False, num_keep_layers=1)).eval()
+    p0 = torch.zeros(0, 5, 3, 16, 16)
+    q, aux = m((p0, p0), (torch.zeros(0, 5, 2),) * 2, (None, None))
+    assert q.shape == (0,) and q.dtype == torch.float32 and aux is None
+    with pytest.raises(ValueError, match="same shape"):
+        m((torch.zeros(1, 5, 3, 16, 16), torch.zeros(1, 4, 3, 16, 16)), (torch.zeros(1, 5, 2),) * 2, (None, None))
+    with pytest.raises(ValueError, match="at least one patch"):
+        m((torch.zeros(1, 0, 3, 16, 16),) * 2, (torch.zeros(1, 0, 2),) * 2, (None, None))

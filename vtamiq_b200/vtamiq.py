@@ -128,6 +128,10 @@ class VTAMIQ(VisionTransformerBackbone):
         B, N = p_ref.shape[0], p_ref.shape[1]
         if patches[1].shape != p_ref.shape:
             raise ValueError("ref and dist patch tensors must have the same shape")
+        if B == 0:   # empty batch: the reference returns an empty score vector (every op is batch-wise)
+            return p_ref.new_empty((0,), dtype=torch.float32), None
+        if N == 0:
+            raise ValueError("vtamiq_b200.VTAMIQ needs at least one patch per image")
         with torch.no_grad():
             ws = eng.workspace(B, N)
             embedded = eng.stage_patches(ws, patches, pos, scales)
