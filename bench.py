@@ -169,7 +169,7 @@ def run_reference_arm(args):
         "e2e": {"value": rate, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -195,10 +195,20 @@ def run_gpu_arm(args):
         sets.append((images.to(dev), [torch.from_numpy(samples).to(dev)]))
     total_pairs = B * world
 
+    # Pairs are independent: the ranks run their batches with NO per-step collective; every step's scores
+    # stay in a device buffer and ONE all_gather at the end of the timed region hands all of them to every rank.
+    score_buf = torch.empty(max(args.steps, 1), B, dtype=torch.float32, device=dev)
+
     def step(i):
         images, samples = sets[i & 1]
         q = model.forward_from_images(images, samples)
-        return gather_scores(q, total_pairs) if world > 1 else q
+        score_buf[i % score_buf.shape[0]].copy_(q)
+        return q
+
+    def collect(n_steps):
+        """all ranks' scores of the last n_steps steps, (n_steps * total_pairs,) in (rank, step, pair) order"""
+        flat = score_buf[:n_steps].reshape(-1)
+        return gather_scores(flat, flat.numel() * world) if world > 1 else flat
 
     def barrier():
         if world > 1:
@@ -223,15 +233,18 @@ def run_gpu_arm(args):
 
     for i in range(max(args.warmup, 3)):
         step(i)
+    collect(min(max(args.warmup, 3), args.steps))   # the collective is warm too
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for i in range(args.steps):
-        q = step(i)
+        step(i)
+    all_scores = collect(args.steps)
     ev1.record()
     barrier()
+    assert all_scores.numel() == args.steps * total_pairs
     clocks = sampler.result()
     ms = ev0.elapsed_time(ev1)
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -292,9 +305,7 @@ def run_gpu_arm(args):
             ev = torch.cuda.Event()
             ev.record()
             done_compute[i & 1] = ev
-            if world > 1:
-                qd = gather_scores(qd, total_pairs)[rank * B:(rank + 1) * B]
-            q_host.copy_(qd, non_blocking=True)
+            q_host.copy_(qd, non_blocking=True)   # this rank's scores; ranks exchange nothing per step
             ready = nxt
         torch.cuda.synchronize()
 
@@ -394,7 +405,7 @@ def run_gpu_arm(args):
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": WORKLOAD if B == PAIRS else WORKLOAD_SWEEP.format(B), "pairs_per_gpu": B, "patches": N_PATCH, "image_hw": [H_IMG, W_IMG],
                        "operands": f"{args.dtype} tcgen05 operands, fp32 accumulate/residual/LN/softmax/DiffNet",
-                       "parallelism": f"dp{world} (pairs sharded, weight replicas, score all_gather only)",
+                       "parallelism": f"dp{world} (pairs sharded, weight replicas, one score all_gather per run)",
                        "cuda_graph": not args.no_graph,
                        "l2": "no explicit flush: per-step working set ~0.7 GB (activations) + 151 MB images, "
                              "two alternating input sets, >> 126 MB L2"},
@@ -411,13 +422,34 @@ def run_gpu_arm(args):
             "launches_per_step": int(launches_per_step),
             "roofline": roofline, "kernels": breakdown, "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_RESULT_OUT = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line, but libraries write there too (NCCL prints its version banner to
+    fd 1).  Keep a private handle on the real stdout for the result and point fd 1 / sys.stdout at stderr."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        sys.stdout = sys.stderr
+
+
+def emit(line: dict):
+    out = _RESULT_OUT if _RESULT_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
