@@ -35,7 +35,7 @@ namespace vtq {
 constexpr int ATT_BQ = 128;   // query rows per tile (two tiles per CTA)
 constexpr int ATT_BKV = 128;  // keys per tile
 constexpr int ATT_D = 64;
-constexpr int ATT_THREADS = 3 * 128;  // warpgroup 0: TMA + MMA warps (+2 idle), warpgroups 1, 2: softmax A, B
+constexpr int ATT_THREADS = 3 * 128;  // warpgroup 0: TMA + two MMA warps (+1 idle), warpgroups 1, 2: softmax A, B
 constexpr int ATT_TILE_BYTES = 128 * ATT_D * 2;  // 16 KB: a 128-row x 64 x 16-bit tile
 constexpr int ATT_KV_STAGES = 3;
 constexpr int ATT_OUT_BYTES = ATT_BQ * ATT_D * 2;  // 16 KB output staging per query tile (4 warps x 32 rows x 128 B)
@@ -48,7 +48,7 @@ constexpr uint32_t ATT_TMEM_O = 256;  // + t * 64
 constexpr uint32_t ATT_TMEM_P = 384;  // + t * 64: P_t as the K-major A operand of P V (two 16-bit keys per column)
 
 // Diagnostics (vtq_attention_fwd_trace): CTA 0 records clock64() at pipeline events; slot layout
-// trace[role * 512 + event_index], role 0 = MMA thread, 1 = softmax A (warp 4 lane 0), 2 = softmax B.
+// trace[role * 512 + event_index], role 0 = MMA thread of tile A, 1 = softmax A (warp 4 lane 0), 2 = softmax B.
 #define ATT_TRACE(role, idx)                                                                     \
   do {                                                                                           \
     if (trace != nullptr && blockIdx.x == 0 && (idx) < 512) trace[(role) * 512 + (idx)] = clock64(); \
@@ -66,12 +66,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
   uint8_t* sO = sV + ATT_KV_STAGES * ATT_TILE_BYTES;   // [2 tiles] output staging of each work item
   uint64_t* bars = reinterpret_cast<uint64_t*>(sO + 2 * ATT_OUT_BYTES);
   uint64_t* q_full = bars;            // [2] Q pair of a work item landed            (TMA tx)
-  uint64_t* q_empty = bars + 2;       // [2] all Q K^T of that work item retired     (MMA commit)
+  uint64_t* q_empty = bars + 2;       // [2] all Q K^T of that work item retired     (2 MMA commits)
   uint64_t* kv_full = bars + 4;       // [3]
-  uint64_t* kv_empty = bars + 7;      // [3]
+  uint64_t* kv_empty = bars + 7;      // [3]                                         (2 MMA commits)
   uint64_t* s_full = bars + 10;       // [2] S_t(n) complete                         (MMA commit)
   uint64_t* s_free = bars + 12;       // [2] S_t(n) copied to registers              (128 arrivals)
-  uint64_t* p_full = bars + 14;       // [2] P_t(n) in smem, O_t rescaled            (128 arrivals)
+  uint64_t* p_full = bars + 14;       // [2] P_t(n) in tensor memory, O_t rescaled   (128 arrivals)
   uint64_t* pv_done = bars + 16;      // [2] O_t += P_t(n) V complete                (MMA commit)
   uint64_t* o_free = bars + 18;       // [2] O_t of a finished work item read out    (128 arrivals)
   uint64_t* xu_turn = bars + 20;      // [2] exponential phases of the two groups alternate (4 warp arrivals)
