@@ -122,7 +122,27 @@ def forward_case(name, vit_cfg, vt_kwargs, B, H, W, N, n_scales, ratio):
     print("forward", name, "q =", q.numpy())
 
 
+def correlations_case():
+    """utils/misc/correlations.py:21-51 on seeded score vectors (one with ties, one already in [0,1])."""
+    from utils.misc.correlations import compute_correlations
+    rng = np.random.default_rng(11)
+    out = {}
+    for k, (n, ties) in enumerate([(60, False), (400, True), (25, False)]):
+        a = rng.normal(size=n) * 1.3 + 4.0
+        b = 0.8 * a + rng.normal(size=n) * (0.25 + 0.2 * k) + 0.1 * a ** 2
+        if ties:
+            a, b = np.round(a, 1), np.round(b, 1)
+        c = compute_correlations(a, b)
+        out[f"a{k}"], out[f"b{k}"] = a, b
+        out[f"want{k}"] = np.array([c[key] for key in ("SROCC", "KROCC", "PLCC", "RMSE", "PLCC_NOFIT", "RMSE_NOFIT")])
+        print("correlations", k, out[f"want{k}"])
+    np.savez_compressed(os.path.join(HERE, "correlations.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--correlations-only" in sys.argv:
+        correlations_case()
+        sys.exit(0)
     patches_case("single", 96, 128, 64, 1, 2.0, seed=3)
     patches_case("multi3", 256, 256, 100, 3, 2.0, seed=4)
     patches_case("odd2", 250, 301, 80, 2, 1.75, seed=5)
@@ -131,3 +151,4 @@ if __name__ == "__main__":
     forward_case("scales3", dict(num_scales=3), {}, B=2, H=256, W=256, N=100, n_scales=3, ratio=2.0)
     forward_case("traincfg", dict(num_keep_layers=6, num_extra_tokens=8, use_layer_scale=True),
                  dict(ca_reduction=16), B=2, H=96, W=128, N=64, n_scales=1, ratio=2.0)
+    correlations_case()

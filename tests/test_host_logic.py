@@ -238,3 +238,34 @@ def test_empty_batch_and_shape_errors_need_no_device():
         m((torch.zeros(1, 5, 3, 16, 16), torch.zeros(1, 4, 3, 16, 16)), (torch.zeros(1, 5, 2),) * 2, (None, None))
     with pytest.raises(ValueError, match="at least one patch"):
         m((torch.zeros(1, 0, 3, 16, 16),) * 2, (torch.zeros(1, 0, 2),) * 2, (None, None))
+
+
+def test_device_side_correlations_match_reference_and_scipy(golden_dir):
+    """vtamiq_b200.metrics against utils/misc/correlations.py of the reference (golden fixture made by
+    tests/golden/make_golden.py) and, for ties, against scipy directly."""
+    import os
+    import numpy as np
+    import scipy.stats
+    import torch
+    from vtamiq_b200 import metrics as M
+    z = np.load(os.path.join(golden_dir, "correlations.npz"))
+    keys = ("SROCC", "KROCC", "PLCC", "RMSE", "PLCC_NOFIT", "RMSE_NOFIT")
+    for k in range(3):
+        a, b = torch.from_numpy(z[f"a{k}"]), torch.from_numpy(z[f"b{k}"])
+        got = M.compute_correlations(a, b)
+        want = dict(zip(keys, z[f"want{k}"]))
+        for key in ("SROCC", "KROCC", "PLCC_NOFIT", "RMSE_NOFIT"):        # closed-form: to rounding
+            assert abs(got[key] - want[key]) < 1e-10, (k, key, got[key], want[key])
+        for key in ("PLCC", "RMSE"):                                       # behind an iterative least-squares fit
+            assert abs(got[key] - want[key]) < 1e-6, (k, key, got[key], want[key])
+        nofit = M.compute_correlations(a, b, fit=False)
+        assert nofit["PLCC"] == nofit["PLCC_NOFIT"] and nofit["RMSE"] == nofit["RMSE_NOFIT"]
+    rng = np.random.default_rng(5)
+    a = np.round(rng.normal(size=500), 1)
+    b = np.round(0.6 * a + rng.normal(size=500) * 0.7, 1)
+    ta, tb = torch.from_numpy(a), torch.from_numpy(b)
+    assert np.abs(M.average_ranks(ta).numpy() - scipy.stats.rankdata(a)).max() == 0
+    assert abs(float(M.spearman(ta, tb)) - scipy.stats.spearmanr(a, b).correlation) < 1e-12
+    assert abs(float(M.kendall(ta, tb, block=96)) - scipy.stats.kendalltau(a, b).correlation) < 1e-12
+    const = torch.full((7,), 3.0, dtype=torch.float64)
+    assert torch.equal(M.normalize_array(const), torch.zeros(7, dtype=torch.float64))   # degenerate range: shifted only

@@ -10,7 +10,8 @@ from .vtamiq import VTAMIQ, VisionTransformerBackbone  # noqa: F401
 from .patch_sampling import (compute_num_patches_per_scale, compute_patch_num_scales, extract_patches,  # noqa: F401
                              get_iqa_patches)
 from .parallel import gather_scores, shard_pairs  # noqa: F401
+from .metrics import compute_correlations  # noqa: F401
 
 __all__ = ["VTAMIQ", "VisionTransformerBackbone", "get_iqa_patches", "extract_patches",
-           "compute_patch_num_scales", "compute_num_patches_per_scale", "shard_pairs", "gather_scores",
+           "compute_patch_num_scales", "compute_num_patches_per_scale", "shard_pairs", "gather_scores", "compute_correlations",
            "get_vit_config", "VIT_VARIANT_B8", "VIT_VARIANT_B16", "VIT_VARIANT_L16"]
