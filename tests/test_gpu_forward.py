@@ -398,3 +398,16 @@ def test_pairwise_shares_the_reference_encoding():
         qb, _ = m((pr, p2), (sr, s2), (None, None))
         q1, q2 = m.forward_pairwise((pr, p1, p2), (sr, s1, s2), None)
     assert torch.allclose(q1, qa, atol=2e-6) and torch.allclose(q2, qb, atol=2e-6)
+
+
+def test_correlations_stay_on_device():
+    """vtamiq_b200.metrics on CUDA tensors equals the CPU result (which the CPU suite pins to the reference)."""
+    from vtamiq_b200 import metrics as M
+    g = torch.Generator().manual_seed(9)
+    a = torch.round(torch.randn(3000, generator=g, dtype=torch.float64) * 10) / 10
+    b = torch.round((0.7 * a + 0.6 * torch.randn(3000, generator=g, dtype=torch.float64)) * 10) / 10
+    want = M.compute_correlations(a, b, fit=False)
+    got = M.compute_correlations(a.cuda(), b.cuda(), fit=False)
+    for k in want:
+        assert abs(want[k] - got[k]) < 1e-9, (k, want[k], got[k])
+    assert M.spearman(a.cuda(), b.cuda()).device.type == "cuda"
