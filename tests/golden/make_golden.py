@@ -139,9 +139,25 @@ def correlations_case():
     np.savez_compressed(os.path.join(HERE, "correlations.npz"), **out)
 
 
+def sampler_draws_case():
+    """Raw draws of the reference's default coordinate sampler (PERTURBED_SIMPLE): the statistical yardstick for
+    vtamiq_b200.patch_sampling.perturbed_grid_samples."""
+    out = {}
+    for name, (h, w, n, draws) in dict(cfg2=(384, 512, 500, 24), small=(96, 128, 64, 100), tall=(300, 100, 37, 100)).items():
+        np.random.seed(1234)
+        smp = sampler()
+        out[name] = np.stack([smp.get_sample_params(h, w, 16, 16, num_samples=n) for _ in range(draws)]).astype(np.float32)
+        out[name + "_hwn"] = np.array([h, w, n])
+        print("sampler draws", name, out[name].shape)
+    np.savez_compressed(os.path.join(HERE, "sampler_draws.npz"), **out)
+
+
 if __name__ == "__main__":
     if "--correlations-only" in sys.argv:
         correlations_case()
+        sys.exit(0)
+    if "--sampler-only" in sys.argv:
+        sampler_draws_case()
         sys.exit(0)
     patches_case("single", 96, 128, 64, 1, 2.0, seed=3)
     patches_case("multi3", 256, 256, 100, 3, 2.0, seed=4)
@@ -152,3 +168,4 @@ if __name__ == "__main__":
     forward_case("traincfg", dict(num_keep_layers=6, num_extra_tokens=8, use_layer_scale=True),
                  dict(ca_reduction=16), B=2, H=96, W=128, N=64, n_scales=1, ratio=2.0)
     correlations_case()
+    sampler_draws_case()

@@ -411,3 +411,20 @@ def test_correlations_stay_on_device():
     for k in want:
         assert abs(want[k] - got[k]) < 1e-9, (k, want[k], got[k])
     assert M.spearman(a.cuda(), b.cuda()).device.type == "cuda"
+
+
+def test_device_sampled_coordinates_feed_the_forward():
+    """Coordinates drawn on the GPU (vtamiq_b200.sample_batch, the reference's default sampler law) go straight into
+    forward_from_images; the scores match the oracle evaluated on the very same coordinates (3 pyramid levels)."""
+    from vtamiq_b200 import sample_batch
+    B, H, W, N = 2, 256, 256, 100
+    m = _build(dict(num_scales=3), {}).cuda()
+    images, _ = _pairs(B, H, W, (1,), seed=21)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    samples = sample_batch(B, H, W, N, 16, 3, 2.0, device="cuda", generator=g)
+    assert [t.shape[-1] for t in samples] == [75, 20, 5] and all(t.is_cuda and t.dtype == torch.float64 for t in samples)
+    with torch.no_grad():
+        q = m.forward_from_images(images.cuda(), samples).cpu()
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    want = _oracle_scores(sd, images, [t.cpu().numpy() for t in samples])
+    assert (q - torch.as_tensor(want)).abs().max().item() <= SCORE_TOL

@@ -269,3 +269,39 @@ def test_device_side_correlations_match_reference_and_scipy(golden_dir):
     assert abs(float(M.kendall(ta, tb, block=96)) - scipy.stats.kendalltau(a, b).correlation) < 1e-12
     const = torch.full((7,), 3.0, dtype=torch.float64)
     assert torch.equal(M.normalize_array(const), torch.zeros(7, dtype=torch.float64))   # degenerate range: shifted only
+
+
+def test_device_coordinate_sampler_has_the_reference_law(golden_dir):
+    """vtamiq_b200.patch_sampling.perturbed_grid_samples vs raw draws of the reference's default
+    sampler (tests/golden/sampler_draws.npz): same support, same one-sample-per-grid-cell structure, same jitter
+    range, and marginals that a two-sample Kolmogorov-Smirnov test cannot tell apart."""
+    import os
+    import numpy as np
+    import scipy.stats
+    import torch
+    from vtamiq_b200.patch_sampling import perturbed_grid_samples, sample_batch
+    z = np.load(os.path.join(golden_dir, "sampler_draws.npz"))
+    g = torch.Generator().manual_seed(3)
+    for name in ("cfg2", "small", "tall"):
+        ref = z[name].astype(np.float64)                       # (draws, 2, n)
+        h, w, n = (int(v) for v in z[name + "_hwn"])
+        ours = perturbed_grid_samples(ref.shape[0], h, w, 16, 16, n, device="cpu", generator=g).numpy()
+        assert ours.shape == ref.shape and ours.dtype == np.float64
+        width = max(int(np.ceil(np.sqrt(n / (h / w)))), 1)
+        height = int(np.ceil(width * h / w))
+        for smp in (ours, ref):
+            assert smp[:, 0].min() >= 0 and smp[:, 0].max() <= h - 16 and smp[:, 1].min() >= 0 and smp[:, 1].max() <= w - 16
+            cy = np.minimum(np.floor(smp[:, 0] / (h - 16) * height), height - 1)
+            cx = np.minimum(np.floor(smp[:, 1] / (w - 16) * width), width - 1)
+            cell = (cy * width + cx).astype(int)
+            assert all(len(set(row)) == n for row in cell)     # n distinct grid cells per image
+            off_y = smp[:, 0] / (h - 16) * height - cy - 0.5   # jitter inside the cell, |.| <= 2 * 0.2
+            off_x = smp[:, 1] / (w - 16) * width - cx - 0.5
+            assert np.abs(off_y).max() <= 0.4 + 1e-6 and np.abs(off_x).max() <= 0.4 + 1e-6
+        for axis in (0, 1):
+            p = scipy.stats.ks_2samp(ours[:, axis].ravel(), ref[:, axis].ravel()).pvalue
+            assert p > 1e-3, (name, axis, p)
+    # multi-scale budget: same level count / per-level counts as the host path, finest level first
+    levels = sample_batch(3, 1024, 1024, 500, 16, 3, 2.0, device="cpu", generator=g)
+    assert [t.shape for t in levels] == [(3, 2, 380), (3, 2, 96), (3, 2, 24)]
+    assert float(levels[2][:, 0].max()) <= 256 - 16

@@ -45,6 +45,54 @@ def compute_num_patches_per_scale(patch_count, patch_num_scales, scale_num_sampl
     return counts
 
 
+def perturbed_grid_samples(batch: int, h: int, w: int, ho: int, wo: int, num_samples: int, *, device="cuda",
+                           generator: torch.Generator | None = None, perturbed_amount: float = 0.2) -> torch.Tensor:
+    """Top-left patch coordinates for ``batch`` images at once, drawn ON THE DEVICE with the law of the reference's
+    default sampler: ``PatchSampler(grid_type=GRID_TYPE_PERTURBED_SIMPLE)`` →
+    ``stratified_grid_sampling`` (patch_sampling.py:236-237, :308-327, :362-376).  That mode is one cell covering the
+    image: a regular ``height x width`` grid with ``width = ceil(sqrt(n / (h/w)))``, ``height = ceil(width * h/w)``,
+    ``n`` DISTINCT grid points chosen uniformly, each jittered by U(-2a, 2a) cells (a = perturbed_amount), moved to
+    the cell centre, clipped to [0, 1] and scaled to [0, h-ho] x [0, w-wo].
+
+    Not bit-reproducible against numpy's RNG stream — the parity definition is statistical (same support, same
+    marginals; tests/test_host_logic.py compares against draws of the reference itself).  Returns float64
+    (batch, 2, num_samples), row 0 = y, the layout ``forward_from_images`` takes.
+    """
+    if num_samples < 1:
+        raise ValueError("num_samples must be positive")
+    aspect = h / w
+    width = max(int(np.ceil(np.sqrt(num_samples / aspect))), 1)
+    height = int(np.ceil(width * aspect))
+    cells = height * width                       # >= num_samples by construction
+    kw = dict(device=device, generator=generator)
+    # n distinct grid points per image: the first n entries of a uniform random permutation
+    picks = torch.rand(batch, cells, **kw).argsort(dim=1)[:, :num_samples]
+    gy = (picks % height).double()               # the reference flattens its (2, width, height) grid this way
+    gx = (picks // height).double()
+    jitter = (2.0 * torch.rand(batch, 2, num_samples, dtype=torch.float64, **kw) - 1.0) * (2.0 * perturbed_amount)
+    py = ((gy + jitter[:, 0]) / height + 0.5 / height).clamp_(0.0, 1.0)
+    px = ((gx + jitter[:, 1]) / width + 0.5 / width).clamp_(0.0, 1.0)
+    return torch.stack([py * (h - ho), px * (w - wo)], dim=1)
+
+
+def sample_batch(batch: int, h: int, w: int, patch_count: int, patch_dim: int = 16, patch_num_scales: int = 1,
+                 scale_num_samples_ratio: float = DEFAULT_NUM_SAMPLES_RATIO, *, device="cuda",
+                 generator: torch.Generator | None = None):
+    """Per-scale coordinate sets for a whole batch, ready for ``VTAMIQ.forward_from_images(images, samples)``:
+    the level count and the per-level patch budget follow the reference (patch_sampling.py:398-411, :427-447; finest
+    level first, level s drawn in the (h >> s, w >> s) image like :575-600)."""
+    n_scales = compute_patch_num_scales(patch_num_scales, h, w, patch_dim, patch_dim)
+    counts = compute_num_patches_per_scale(patch_count, n_scales, scale_num_samples_ratio)[::-1]
+    out, total = [], 0
+    for lvl, n in enumerate(counts):
+        out.append(perturbed_grid_samples(batch, h >> lvl, w >> lvl, patch_dim, patch_dim, int(n), device=device,
+                                          generator=generator))
+        total += int(n)
+        if total >= patch_count:   # the reference stops as soon as the budget is spent (:606-607)
+            break
+    return out
+
+
 def _pyramid(ctx, level0: torch.Tensor, num_levels: int):
     """[planes..., H, W] fp32 -> list of levels; level s+1 = 2x2 mean of level s (floor mode)."""
     levels = [level0]
