@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VTQ_ABI_VERSION 2
+#define VTQ_ABI_VERSION 3
 
 enum vtq_status {
   VTQ_OK = 0,
@@ -55,6 +55,14 @@ int vtq_destroy(vtq_ctx* ctx);
 const char* vtq_last_error_string(const vtq_ctx* ctx); /* ctx may be NULL: error of the last failed vtq_create */
 /* number of kernels launched through this handle since creation (monotonic) */
 unsigned long long vtq_launch_count(const vtq_ctx* ctx);
+/* Coordinate-range status of the gather kernels (vtq_patch_gather*): 1 if any launch since the last reset saw a
+ * patch origin outside [0, H-16] x [0, W-16] (or NaN) — torch raises IndexError for those in the reference's gather
+ * (data/patch_sampling.py:531-545); here the origin is clamped into the image and this flag is raised instead.  The
+ * flag lives in pinned, mapped host memory: reading it needs no synchronisation, but it only reflects kernels that
+ * have finished.  reset != 0 clears it. */
+int vtq_coord_status(vtq_ctx* ctx, int reset);
+/* TMA descriptor cache of this handle (descriptors are encoded once per distinct (pointer, shape, box) and re-used) */
+int vtq_tensor_map_stats(const vtq_ctx* ctx, unsigned long long* hits, unsigned long long* misses);
 /* bytes of scratch vtq_diffnet_head needs for a batch of B pairs */
 int64_t vtq_workspace_bytes(const vtq_ctx* ctx, int B, int hidden);
 
@@ -77,13 +85,19 @@ int vtq_patch_gather(vtq_ctx* ctx, const float* images, int n_img, int H, int W,
 /* K1 with the image transform fused in (SURVEY §8f "next" #2).  images [n_img][H][W][3] uint8 (as decoded); each
  * pixel goes through the reference's transform_img arithmetic — x/255, then (x-0.5)/0.5, fp32, in that order
  * (data/utils.py:76,:94; data/patch_datasets.py:51-52) — inside the gather, so outputs are bit-identical to gathering
- * from the transformed fp32 tensor.  Single level (all n patches of N_total = n). */
+ * from the transformed fp32 tensor.  Same slot / uv / scale-id conventions as vtq_patch_gather (level 0 of a pyramid
+ * is gathered straight from the uint8 image; coarser levels come from vtq_avgpool2x2_u8 / vtq_avgpool2x2). */
 int vtq_patch_gather_u8(vtq_ctx* ctx, const uint8_t* images, int n_img, int H, int W, const double* samples, int n_set,
-                        int n, float* patches_f32, void* patches_16, int dtype, float* pos, void* stream);
+                        int n, int patch_offset, int N_total, float* patches_f32, void* patches_16, int dtype,
+                        float* pos, float* scales, int scale_id, void* stream);
 
-/* The same transform for whole images: uint8 [n_img][H][W][3] -> fp32 [n_img][3][H][W]; only needed in front of the
- * pyramid when more than one scale is sampled. */
+/* The same transform for whole images: uint8 [n_img][H][W][3] -> fp32 [n_img][3][H][W]. */
 int vtq_normalize_u8(vtq_ctx* ctx, const uint8_t* src, float* dst, int n_img, int H, int W, void* stream);
+
+/* Pyramid level 1 straight from the decoded image: transform (as above) then 2x2 mean, i.e.
+ * AvgPool2d(2)(transform(img)) of data/patch_sampling.py:552,:600 without materialising the fp32 level-0 image.
+ * src uint8 [n_img][H][W][3] -> dst fp32 [n_img][3][H/2][W/2].  Needs W % 8 == 0. */
+int vtq_avgpool2x2_u8(vtq_ctx* ctx, const uint8_t* src, float* dst, int n_img, int H, int W, void* stream);
 
 /* 2x2 mean pyramid level, floor mode, summation order ((a00+a01)+a10)+a11 then *0.25
  * replaces nn.AvgPool2d(2) at data/patch_sampling.py:552,:600.  src [planes][H][W] -> dst [planes][H/2][W/2] */
@@ -183,6 +197,32 @@ int vtq_cls_diff(vtq_ctx* ctx, const float* x_ref, const float* x_dist, int B, i
 int vtq_diffnet_head(vtq_ctx* ctx, const float* diff, const void* const* params, int n_params, int num_rgs,
                      int num_rcabs, int hidden, int ca_hidden, int head_hidden, int B, float* q, void* workspace,
                      void* stream);
+
+/* ---- K8 with a backward pass: frozen-encoder fine-tuning (SURVEY §8f "next" #1, first slice) --------------------
+ * replaces, for the parameters behind the encoder, what torch.autograd does in train.py:317-322 when the encoder is
+ * frozen (modules/vtamiq/vtamiq.py:81-92, modules/VisionTransformer/backbone.py:62-106).  All fp32.
+ *
+ * vtq_tail_train_fwd: q = head(DiffNet(gamma * d0)) like vtq_diffnet_head, but every activation the backward pass
+ *   needs is kept in `saved` (vtq_tail_saved_floats(...) floats).
+ *     d0         [B][hidden]  LN(cls_ref) - LN(cls_dist), i.e. vtq_cls_diff with gamma = NULL
+ *     gamma      [hidden] or NULL (diff_scale=False)
+ *     drop_scale [num_rgs][B] or NULL: DropPath of each ResidualGroup branch (channel_attention.py:26-29) as a per-pair
+ *                factor mask/keep_prob; NULL = evaluation mode (identity)
+ *     workspace  >= 32 KB (barrier counters of the fused decoder)
+ * vtq_tail_bwd: given dq [B] = dLoss/dq, writes dLoss/dparam for every entry of `params` into the matching entry of
+ *   `grads` (HOST array of device pointers, same order and shapes as params; an entry may be NULL = not wanted),
+ *   dgamma [hidden] (or NULL) and d_d0 [B][hidden] (or NULL; the gradient that would flow on into the encoder).
+ *   Gradients are written, not accumulated.  workspace >= vtq_tail_bwd_workspace_bytes(B, hidden).
+ *   Reductions run in a fixed order (no atomics): results are bit-reproducible. */
+int64_t vtq_tail_saved_floats(int B, int num_rgs, int num_rcabs, int hidden, int ca_hidden, int head_hidden);
+int64_t vtq_tail_bwd_workspace_bytes(int B, int hidden);
+int vtq_tail_train_fwd(vtq_ctx* ctx, const float* d0, const float* gamma, const void* const* params, int n_params,
+                       int num_rgs, int num_rcabs, int hidden, int ca_hidden, int head_hidden, int B,
+                       const float* drop_scale, float* saved, float* q, void* workspace, void* stream);
+int vtq_tail_bwd(vtq_ctx* ctx, const float* dq, const float* d0, const float* gamma, const void* const* params,
+                 void* const* grads, int n_params, int num_rgs, int num_rcabs, int hidden, int ca_hidden,
+                 int head_hidden, int B, const float* drop_scale, const float* saved, float* dgamma, float* d_d0,
+                 void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

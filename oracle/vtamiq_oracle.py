@@ -106,8 +106,11 @@ def vit_tokens(sd, cfg, patches, pos, scales, return_layers=False):
     return (out, states) if return_layers else out
 
 
-def diffnet_head(sd, cfg, d):
-    """d (B,H) = gamma*(cls_ref - cls_dist) -> q (B,).  1x1 Conv1d on a length-1 signal == F.linear."""
+def diffnet_head(sd, cfg, d, drop_scale=None):
+    """d (B,H) = gamma*(cls_ref - cls_dist) -> q (B,).  1x1 Conv1d on a length-1 signal == F.linear.
+    drop_scale (num_rgs, B) or None: training-mode DropPath of each ResidualGroup branch as the per-pair factor
+    mask/keep_prob (channel_attention.py:26-29 ``x + self.drop(self.body(x))``; timm DropPath).  Differentiable:
+    tests run it under torch.autograd to check the CUDA backward."""
     lin = lambda x, w, b: F.linear(x, sd[w].squeeze(-1), sd[b])
     x = d
     for g in range(cfg["num_rgs"]):
@@ -119,7 +122,10 @@ def diffnet_head(sd, cfg, d):
             w = torch.sigmoid(lin(w, p + "4.conv_du.4.weight", p + "4.conv_du.4.bias"))
             x = x + y * w
         p = f"quality_decoder.{g}.body.{cfg['num_rcabs']}."
-        x = skip + lin(x, p + "weight", p + "bias")
+        branch = lin(x, p + "weight", p + "bias")
+        if drop_scale is not None:
+            branch = branch * drop_scale[g][:, None]
+        x = skip + branch
     if cfg["num_rgs"]:
         p = f"quality_decoder.{cfg['num_rgs']}."
         x = lin(x, p + "weight", p + "bias")

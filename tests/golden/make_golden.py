@@ -152,7 +152,83 @@ def sampler_draws_case():
     np.savez_compressed(os.path.join(HERE, "sampler_draws.npz"), **out)
 
 
+def load_from_case():
+    """The reference's own npz loader (transformer.py:643-668 -> :287-325, :428-455) on a synthetic JAX-format
+    checkpoint: once with a 577-token positional table (copied as is) and once with a 197-token one (14x14 grid ->
+    ndimage.zoom to 24x24).  The fixture keeps the state_dict hash and the complete resized positional table."""
+    out = {}
+    for tag, ntok in (("same", 577), ("zoom", 197)):
+        torch.manual_seed(0)
+        model = VTAMIQ(vit_config=dict(pretrained=False)).eval()
+        w = synth.synthetic_vit_npz(seed=21, pos_tokens=ntok)
+        model.transformer.load_from(w, True, True)
+        sd = model.state_dict()
+        out[f"hash_{tag}"] = synth.state_hash(sd)
+        out[f"pos_{tag}"] = sd["transformer.embeddings.positional_embeddings.positional_embeddings"].numpy()[0, ::7].copy()
+        print("load_from", tag, out[f"hash_{tag}"][:16])
+    np.savez_compressed(os.path.join(HERE, "load_from.npz"), **out)
+
+
+def tail_grads_case():
+    """Gradients the REFERENCE's autograd gives the parameters behind the encoder (diff_scale, quality_decoder,
+    q_predictor) for loss = sum_b w_b q_b: evaluation mode (DropPath identity) and training mode (DropPath masks
+    drawn from torch's CPU generator after manual_seed(77): the fixture records them through a hook).
+    The encoder is frozen like set_freeze_state does (backbone.py:62-106); its output difference d0 is recorded so
+    the tail can be re-run on its own."""
+    vit_cfg, vt_kwargs = dict(num_keep_layers=1), dict(num_rgs=2, num_rcabs=2)
+    B, N = 5, 12
+    g = torch.Generator().manual_seed(3)
+    patches = [torch.randn(B, N, 3, 16, 16, generator=g) for _ in range(2)]
+    pos = [torch.rand(B, N, 2, generator=g) * 0.999 for _ in range(2)]
+    wts = torch.linspace(0.5, 1.5, B)
+    out = dict(vit_cfg=repr(vit_cfg), vt_kwargs=repr(vt_kwargs), B=B, wts=wts.numpy())
+    for mode in ("eval", "train"):
+        torch.manual_seed(0)
+        model = VTAMIQ(vit_config=dict(pretrained=False, **vit_cfg), **vt_kwargs)
+        synth.perturb_(model)
+        with torch.no_grad():   # make every tail parameter class matter (biases, PReLU slopes)
+            gen = torch.Generator().manual_seed(9)
+            for name, p in model.named_parameters():
+                if name.startswith(("quality_decoder", "q_predictor")) and name.endswith("bias"):
+                    p.copy_(0.05 * torch.randn(p.shape, generator=gen))
+        for p in model.transformer.parameters():
+            p.requires_grad = False
+        model.train(mode == "train")
+        rec, masks = {}, []
+        h = model.diff_scale.register_forward_pre_hook(lambda m, inp: rec.__setitem__("d0", inp[0].detach().clone()))
+        hooks = [h]
+        for grp in list(model.quality_decoder)[:-1]:
+            def post(mod, inp, outp, grp=grp):
+                # DropPath output / input = the per-sample factor (mask / keep_prob)
+                ratio = (outp / inp[0]).detach()
+                masks.append(torch.nan_to_num(ratio[:, 0, 0], nan=0.0))
+            hooks.append(grp.drop.register_forward_hook(post))
+        torch.manual_seed(77)
+        q, _ = model((patches[0], patches[1]), (pos[0], pos[1]), (None, None))
+        (q * wts).sum().backward()
+        for hk in hooks:
+            hk.remove()
+        out[f"state_hash_{mode}"] = synth.state_hash(model.state_dict())
+        out[f"d0_{mode}"] = rec["d0"].numpy()
+        out[f"q_{mode}"] = q.detach().numpy()
+        out[f"drop_{mode}"] = torch.stack(masks).numpy()
+        names = []
+        for name, p in model.named_parameters():
+            if p.grad is not None:
+                names.append(name)
+                out[f"grad_{mode}/{name}"] = synth.grad_probe(p.grad)
+        out[f"names_{mode}"] = np.array(names)
+        print("tail grads", mode, len(names), "params; drop factors", out[f"drop_{mode}"].tolist())
+    np.savez_compressed(os.path.join(HERE, "tail_grads.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--load-from-only" in sys.argv:
+        load_from_case()
+        sys.exit(0)
+    if "--tail-grads-only" in sys.argv:
+        tail_grads_case()
+        sys.exit(0)
     if "--correlations-only" in sys.argv:
         correlations_case()
         sys.exit(0)
@@ -169,3 +245,5 @@ if __name__ == "__main__":
                  dict(ca_reduction=16), B=2, H=96, W=128, N=64, n_scales=1, ratio=2.0)
     correlations_case()
     sampler_draws_case()
+    load_from_case()
+    tail_grads_case()

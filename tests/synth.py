@@ -117,3 +117,39 @@ def select_separated(scores: np.ndarray, k: int, min_gap: float) -> np.ndarray:
         raise ValueError(f"only {len(chosen)} of the requested {k} pairs are {min_gap} apart")
     pick = np.round(np.linspace(0, len(chosen) - 1, k)).astype(int)
     return np.sort(np.array(chosen)[pick])
+
+
+def synthetic_vit_npz(seed: int = 0, pos_tokens: int = 577, hidden: int = 768, mlp: int = 3072, heads: int = 12,
+                      layers: int = 12, patch: int = 16) -> dict:
+    """A JAX-format ViT checkpoint (the key/shape layout of Google's ViT-B_16.npz that
+    ``VisionTransformer.load_from`` reads, transformer.py:287-325,:428-455,:643-668) filled with seeded noise.
+    ``pos_tokens`` = 197 gives a 14x14 positional grid, which makes load_from take its ndimage.zoom resize branch."""
+    rng = np.random.default_rng(seed)
+    f = lambda *s: rng.standard_normal(s, dtype=np.float32)
+    d = hidden // heads
+    w = {"embedding/kernel": f(patch, patch, 3, hidden), "embedding/bias": f(hidden), "cls": f(1, 1, hidden),
+         "Transformer/posembed_input/pos_embedding": f(1, pos_tokens, hidden),
+         "Transformer/encoder_norm/scale": f(hidden), "Transformer/encoder_norm/bias": f(hidden)}
+    for i in range(layers):
+        r = f"Transformer/encoderblock_{i}/"
+        for n in ("query", "key", "value"):
+            w[r + f"MultiHeadDotProductAttention_1/{n}/kernel"] = f(hidden, heads, d)
+            w[r + f"MultiHeadDotProductAttention_1/{n}/bias"] = f(heads, d)
+        w[r + "MultiHeadDotProductAttention_1/out/kernel"] = f(heads, d, hidden)
+        w[r + "MultiHeadDotProductAttention_1/out/bias"] = f(hidden)
+        w[r + "MlpBlock_3/Dense_0/kernel"] = f(hidden, mlp)
+        w[r + "MlpBlock_3/Dense_0/bias"] = f(mlp)
+        w[r + "MlpBlock_3/Dense_1/kernel"] = f(mlp, hidden)
+        w[r + "MlpBlock_3/Dense_1/bias"] = f(hidden)
+        for n in ("LayerNorm_0", "LayerNorm_2"):
+            w[r + n + "/scale"] = f(hidden)
+            w[r + n + "/bias"] = f(hidden)
+    return w
+
+
+def grad_probe(t) -> np.ndarray:
+    """Compact fingerprint of a gradient tensor for fixtures: [sum, sum|.|, 24 strided samples]."""
+    a = t.detach().cpu().double().reshape(-1).numpy()
+    idx = np.unique(np.linspace(0, a.size - 1, 24).round().astype(np.int64))
+    pad = np.full(24 - idx.size, np.nan)
+    return np.concatenate([[a.sum(), np.abs(a).sum()], a[idx], pad])

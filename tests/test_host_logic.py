@@ -232,12 +232,48 @@ def test_empty_batch_and_shape_errors_need_no_device():
     import vtamiq_b200
     m = vtamiq_b200.VTAMIQ(vit_config=dict(pretrained=False, num_keep_layers=1)).eval()
     p0 = torch.zeros(0, 5, 3, 16, 16)
-    q, aux = m((p0, p0), (torch.zeros(0, 5, 2),) * 2, (None, None))
-    assert q.shape == (0,) and q.dtype == torch.float32 and aux is None
-    with pytest.raises(ValueError, match="same shape"):
-        m((torch.zeros(1, 5, 3, 16, 16), torch.zeros(1, 4, 3, 16, 16)), (torch.zeros(1, 5, 2),) * 2, (None, None))
-    with pytest.raises(ValueError, match="at least one patch"):
-        m((torch.zeros(1, 0, 3, 16, 16),) * 2, (torch.zeros(1, 0, 2),) * 2, (None, None))
+    with torch.no_grad():
+        q, aux = m((p0, p0), (torch.zeros(0, 5, 2),) * 2, (None, None))
+        assert q.shape == (0,) and q.dtype == torch.float32 and aux is None
+        with pytest.raises(ValueError, match="same shape"):
+            m((torch.zeros(1, 5, 3, 16, 16), torch.zeros(1, 4, 3, 16, 16)), (torch.zeros(1, 5, 2),) * 2, (None, None))
+        with pytest.raises(ValueError, match="at least one patch"):
+            m((torch.zeros(1, 0, 3, 16, 16),) * 2, (torch.zeros(1, 0, 2),) * 2, (None, None))
+
+
+def test_grad_mode_never_returns_a_silently_detached_score():
+    """With autograd recording, the module either has a backward for everything that wants gradients (the tail, with
+    the encoder frozen) or raises — it never hands back a detached score.  Host-side decision only."""
+    import pytest
+    import torch
+    import vtamiq_b200
+    m = vtamiq_b200.VTAMIQ(vit_config=dict(pretrained=False, num_keep_layers=1)).eval()
+    p = torch.zeros(1, 4, 3, 16, 16)
+    pos = torch.zeros(1, 4, 2)
+    with pytest.raises(NotImplementedError, match="encoder parameters require grad"):
+        m((p, p), (pos, pos), (None, None))          # eval mode, grad enabled, every parameter trainable
+    for q in m.transformer.parameters():
+        q.requires_grad = False
+    assert m._grad_mode() == "tail"                  # frozen encoder: the differentiable tail takes over
+    with pytest.raises(NotImplementedError, match="respect to the inputs"):
+        m((p.clone().requires_grad_(True), p), (pos, pos), (None, None))
+    for q in m.parameters():
+        q.requires_grad = False
+    assert m._grad_mode() == "none"
+    with torch.no_grad():
+        assert m._grad_mode() == "none"
+
+
+def test_module_copies_and_pickles_without_its_engine():
+    import copy
+    import pickle
+    import vtamiq_b200
+    m = vtamiq_b200.VTAMIQ(vit_config=dict(pretrained=False, num_keep_layers=1), operand_dtype="bf16").eval()
+    c = copy.deepcopy(m)
+    assert c.engine is not m.engine and c.engine.model is c and c.engine.operand_dtype == "bf16"
+    r = pickle.loads(pickle.dumps(m))
+    assert r.engine.model is r and r.engine.operand_dtype == "bf16"
+    assert all((a == b).all() for a, b in zip(m.state_dict().values(), r.state_dict().values()))
 
 
 def test_device_side_correlations_match_reference_and_scipy(golden_dir):
@@ -331,3 +367,44 @@ def test_bench_reference_arm_contract():
         assert key in d, key
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_u8_transform_is_exact():
+    """The vector gather kernels evaluate the reference's image transform — u/255 (to_tensor) then (t-.5)/.5
+    (normalize), each rounded to fp32 — without divisions: q0 = u*r, e = fma(-q0,255,u), q = fma(e,r,q0),
+    z = fma(q,2,-1) with r = RN(1/255) (csrc/gather.cu normalize_u8x2).  Exact rational arithmetic shows both forms
+    round to the same fp32 value for every byte, and that value is what torch computes."""
+    from fractions import Fraction
+    import math
+
+    def rn32(fr):
+        if fr == 0:
+            return Fraction(0)
+        sign, a = (-1 if fr < 0 else 1), abs(fr)
+        e = math.floor(math.log2(float(a)))
+        while Fraction(2) ** e > a:
+            e -= 1
+        while Fraction(2) ** (e + 1) <= a:
+            e += 1
+        ulp = Fraction(2) ** (e - 23)
+        qn = a / ulp
+        n = qn.numerator // qn.denominator
+        rem = qn - n
+        if rem > Fraction(1, 2) or (rem == Fraction(1, 2) and n % 2 == 1):
+            n += 1
+        return sign * n * ulp
+
+    r = rn32(Fraction(1, 255))
+    assert float(r) == float(np.float32(0.003921568859368563))
+    t = torch.arange(256, dtype=torch.float32).div(255).sub_(0.5).div_(0.5).numpy()
+    for u in range(256):
+        U = Fraction(u)
+        want_q = rn32(U / 255)
+        q0 = rn32(U * r)
+        e = U - q0 * 255
+        assert rn32(e) == e                       # the fma residual is exactly representable
+        q = rn32(q0 + e * r)
+        assert q == want_q, u
+        z = rn32(2 * q - 1)
+        assert z == rn32(rn32(want_q - Fraction(1, 2)) * 2), u
+        assert float(z) == float(t[u]), u

@@ -93,3 +93,63 @@ def test_forward_oracle_matches_reference(golden_dir, case):
         np.testing.assert_allclose(st[1][:, [0, -1]].numpy(), g["layer0_tok"][i], rtol=0, atol=2e-5)
     np.testing.assert_allclose(inter["diff"].numpy(), g["diff"], rtol=0, atol=5e-5)
     np.testing.assert_allclose(q.numpy(), g["q"], rtol=0, atol=2e-5)
+
+
+# ------------------------------------------------------------------------------------------ tail gradients
+def _tail_oracle_grads(g, mode):
+    """Oracle tail under torch.autograd on the reference's recorded d0 / DropPath factors."""
+    import ast
+    import vtamiq_b200
+    vit_cfg, vt_kwargs = ast.literal_eval(str(g["vit_cfg"])), ast.literal_eval(str(g["vt_kwargs"]))
+    torch.manual_seed(0)
+    m = vtamiq_b200.VTAMIQ(vit_config=dict(pretrained=False, **vit_cfg), **vt_kwargs)
+    synth.perturb_(m)
+    with torch.no_grad():
+        gen = torch.Generator().manual_seed(9)
+        for name, p in m.named_parameters():
+            if name.startswith(("quality_decoder", "q_predictor")) and name.endswith("bias"):
+                p.copy_(0.05 * torch.randn(p.shape, generator=gen))
+    assert synth.state_hash(m.state_dict()) == str(g[f"state_hash_{mode}"])
+    sd = {k: v.detach().clone().requires_grad_(k.startswith(("quality_decoder", "q_predictor", "diff_scale")))
+          for k, v in m.state_dict().items()}
+    cfg = vtamiq_oracle._cfg_from_state(sd)
+    d0 = torch.from_numpy(g[f"d0_{mode}"])
+    drop = torch.from_numpy(g[f"drop_{mode}"]) if mode == "train" else None
+    q = vtamiq_oracle.diffnet_head(sd, cfg, d0 * sd["diff_scale.gamma"], drop_scale=drop)
+    (q * torch.from_numpy(g["wts"])).sum().backward()
+    return m, sd, q
+
+
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_oracle_tail_gradients_match_reference_autograd(golden_dir, mode):
+    """The oracle's differentiable tail (incl. DropPath factors) reproduces the gradients the REFERENCE's autograd
+    produced (tests/golden/make_golden.py::tail_grads_case) — this pins the checker of the CUDA backward."""
+    g = np.load(os.path.join(golden_dir, "tail_grads.npz"))
+    _, sd, q = _tail_oracle_grads(g, mode)
+    assert np.abs(q.detach().numpy() - g[f"q_{mode}"]).max() < 1e-5
+    names = [str(n) for n in g[f"names_{mode}"]]
+    assert len(names) == 40 and "diff_scale.gamma" in names
+    for name in names:
+        want = g[f"grad_{mode}/{name}"]
+        got = synth.grad_probe(sd[name].grad)
+        ok = ~np.isnan(want)
+        scale = max(np.abs(want[ok][2:]).max(), 1e-6)
+        assert np.abs(got[ok][2:] - want[ok][2:]).max() <= 2e-5 * scale + 1e-7, name
+        assert abs(got[1] - want[1]) <= 1e-4 * want[1] + 1e-6, name
+
+
+# ------------------------------------------------------------------------------------------ npz loader
+@pytest.mark.parametrize("tag,ntok", [("same", 577), ("zoom", 197)])
+def test_load_from_matches_reference_loader(golden_dir, tag, ntok):
+    """VisionTransformer.load_from on a synthetic JAX-format checkpoint gives the state_dict the REFERENCE's loader
+    gave on the same file (hash over every key and tensor), including the ndimage.zoom resize of a 14x14 positional
+    grid (transformer.py:428-455)."""
+    import vtamiq_b200
+    g = np.load(os.path.join(golden_dir, "load_from.npz"))
+    torch.manual_seed(0)
+    m = vtamiq_b200.VTAMIQ(vit_config=dict(pretrained=False)).eval()
+    m.transformer.load_from(synth.synthetic_vit_npz(seed=21, pos_tokens=ntok), True, True)
+    sd = m.state_dict()
+    pos = sd["transformer.embeddings.positional_embeddings.positional_embeddings"].numpy()[0, ::7]
+    assert np.array_equal(pos, g[f"pos_{tag}"])
+    assert synth.state_hash(sd) == str(g[f"hash_{tag}"])

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("VTQ_LIBRARY") or os.path.join(_HERE, "libvtamiq_b200.
 
 VTQ_F16, VTQ_BF16 = 0, 1
 EPI_BIAS_H, EPI_BIAS_GELU_H, EPI_BIAS_F32, EPI_BIAS_RESID_F32 = 0, 1, 2, 3
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
@@ -28,7 +28,10 @@ SIGNATURES = {
     "vtq_launch_count": (C.c_ulonglong, [_vp]),
     "vtq_workspace_bytes": (_i64, [_vp, _i, _i]),
     "vtq_patch_gather": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp]),
-    "vtq_patch_gather_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "vtq_patch_gather_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp]),
+    "vtq_avgpool2x2_u8": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "vtq_coord_status": (_i, [_vp, _i]),
+    "vtq_tensor_map_stats": (_i, [_vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     "vtq_normalize_u8": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "vtq_avgpool2x2": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "vtq_cast_rows": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
@@ -42,6 +45,11 @@ SIGNATURES = {
     "vtq_attention_fwd_trace": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "vtq_cls_diff": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp]),
     "vtq_diffnet_head": (_i, [_vp, _vp, C.POINTER(_vp), _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "vtq_tail_saved_floats": (_i64, [_i, _i, _i, _i, _i, _i]),
+    "vtq_tail_bwd_workspace_bytes": (_i64, [_i, _i]),
+    "vtq_tail_train_fwd": (_i, [_vp, _vp, _vp, C.POINTER(_vp), _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "vtq_tail_bwd": (_i, [_vp, _vp, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp), _i, _i, _i, _i, _i, _i, _i, _vp, _vp,
+                          _vp, _vp, _vp, _vp]),
 }
 
 _lock = threading.Lock()
@@ -92,6 +100,15 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.lib.vtq_launch_count(self.handle))
+
+    def coord_status(self, reset: bool = False) -> int:
+        """1 if a finished gather launch saw an out-of-range patch origin since the last reset (no sync needed)."""
+        return int(self.lib.vtq_coord_status(self.handle, 1 if reset else 0))
+
+    def tensor_map_stats(self) -> tuple[int, int]:
+        h, m = C.c_ulonglong(0), C.c_ulonglong(0)
+        self.lib.vtq_tensor_map_stats(self.handle, C.byref(h), C.byref(m))
+        return int(h.value), int(m.value)
 
     def workspace_bytes(self, B: int, hidden: int) -> int:
         return int(self.lib.vtq_workspace_bytes(self.handle, B, hidden))

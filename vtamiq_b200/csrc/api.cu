@@ -42,12 +42,37 @@ int make_tensor_map(vtq_ctx* ctx, CUtensorMap* out, CUtensorMapDataType dt, int 
   cuuint64_t gstrides[4];
   cuuint32_t gbox[5];
   cuuint32_t estr[5];
+  // cache key = every argument of the encoding (the descriptor is a pure function of them)
+  struct {
+    const void* base;
+    uint64_t dims[5], strides[4];
+    uint32_t box[5];
+    int dt, rank, swz;
+  } key;
+  std::memset(&key, 0, sizeof(key));
+  key.base = base;
+  key.dt = static_cast<int>(dt);
+  key.rank = rank;
+  key.swz = swizzle_64b ? 1 : 0;
   for (int i = 0; i < rank; ++i) {
     gdims[i] = dims[i];
     gbox[i] = box[i];
     estr[i] = 1;
-    if (i > 0) gstrides[i - 1] = strides_bytes[i - 1];
+    key.dims[i] = dims[i];
+    key.box[i] = box[i];
+    if (i > 0) {
+      gstrides[i - 1] = strides_bytes[i - 1];
+      key.strides[i - 1] = strides_bytes[i - 1];
+    }
   }
+  const std::string skey(reinterpret_cast<const char*>(&key), sizeof(key));
+  auto hit = ctx->tensor_maps.find(skey);
+  if (hit != ctx->tensor_maps.end()) {
+    *out = hit->second;
+    ctx->tensor_map_hits++;
+    return VTQ_OK;
+  }
+  ctx->tensor_map_misses++;
   CUresult r = ctx->encode_tiled(out, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdims, gstrides,
                                  gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                  swizzle_64b ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
@@ -61,6 +86,8 @@ int make_tensor_map(vtq_ctx* ctx, CUtensorMap* out, CUtensorMapDataType dt, int 
              box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0);
     return fail(ctx, VTQ_ERR_CUDA, buf);
   }
+  if (ctx->tensor_maps.size() >= 8192) ctx->tensor_maps.clear();  // bound the cache (workspaces come and go)
+  ctx->tensor_maps.emplace(skey, *out);
   return VTQ_OK;
 }
 
@@ -87,7 +114,13 @@ extern "C" int vtq_create(vtq_ctx** out, int device) {
                 std::string("vtq_create: device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
                     std::to_string(prop.minor) + "; the kernels are compiled for sm_100a only");
   }
+  int prev_device = -1;
+  cudaGetDevice(&prev_device);
   if ((e = cudaSetDevice(device)) != cudaSuccess) return check_cuda(nullptr, e, "vtq_create: cudaSetDevice");
+  struct Restore {  // the caller's current device is left as it was
+    int d;
+    ~Restore() { if (d >= 0) cudaSetDevice(d); }
+  } restore{prev_device};
   vtq_ctx* ctx = new vtq_ctx();
   ctx->device = device;
   ctx->num_sms = prop.multiProcessorCount;
@@ -100,12 +133,38 @@ extern "C" int vtq_create(vtq_ctx** out, int device) {
     return fail(nullptr, VTQ_ERR_CUDA, "vtq_create: cuTensorMapEncodeTiled is not available from this driver");
   }
   ctx->encode_tiled = reinterpret_cast<decltype(ctx->encode_tiled)>(fn);
+  // coordinate-range flag of the gather kernels: pinned, mapped host word (the host reads it without a sync)
+  e = cudaHostAlloc(reinterpret_cast<void**>(&ctx->oob_flag_host), sizeof(int), cudaHostAllocMapped);
+  if (e == cudaSuccess) {
+    *ctx->oob_flag_host = 0;
+    e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->oob_flag_dev), ctx->oob_flag_host, 0);
+  }
+  if (e != cudaSuccess) {
+    if (ctx->oob_flag_host) cudaFreeHost(ctx->oob_flag_host);
+    delete ctx;
+    return check_cuda(nullptr, e, "vtq_create: pinned flag allocation");
+  }
   *out = ctx;
   return VTQ_OK;
 }
 
 extern "C" int vtq_destroy(vtq_ctx* ctx) {
+  if (ctx && ctx->oob_flag_host) cudaFreeHost(ctx->oob_flag_host);
   delete ctx;
+  return VTQ_OK;
+}
+
+extern "C" int vtq_coord_status(vtq_ctx* ctx, int reset) {
+  if (!ctx) return VTQ_ERR_INVALID;
+  const int v = *static_cast<volatile int*>(ctx->oob_flag_host);
+  if (reset) *static_cast<volatile int*>(ctx->oob_flag_host) = 0;
+  return v;
+}
+
+extern "C" int vtq_tensor_map_stats(const vtq_ctx* ctx, unsigned long long* hits, unsigned long long* misses) {
+  if (!ctx) return VTQ_ERR_INVALID;
+  if (hits) *hits = ctx->tensor_map_hits;
+  if (misses) *misses = ctx->tensor_map_misses;
   return VTQ_OK;
 }
 
@@ -117,7 +176,7 @@ extern "C" unsigned long long vtq_launch_count(const vtq_ctx* ctx) { return ctx 
 
 extern "C" int vtq_gemm(vtq_ctx* ctx, const void* A, int64_t lda, const void* W, const float* bias, int M, int N,
                         int K, int dtype, int epilogue, void* out, int64_t ldo, const float* gamma, void* stream) {
-  if (!ctx) return VTQ_ERR_INVALID;
+  VTQ_ENTER(ctx);
   return launch_gemm(ctx, A, lda, W, bias, M, N, K, dtype, epilogue, out, ldo, gamma,
                      static_cast<cudaStream_t>(stream));
 }
@@ -126,7 +185,7 @@ extern "C" int vtq_gemm_ln(vtq_ctx* ctx, const void* A, int64_t lda, const void*
                            int K, int dtype, int epilogue, void* out, int64_t ldo, const float* gamma,
                            const float* ln_in, int ln_in_slots, const float* ln_colsum, float ln_eps,
                            void* raw16_out, float* ln_out, void* stream) {
-  if (!ctx) return VTQ_ERR_INVALID;
+  VTQ_ENTER(ctx);
   GemmLnArgs ln = {ln_in, ln_in_slots, ln_colsum, ln_eps, raw16_out, ln_out};
   return launch_gemm(ctx, A, lda, W, bias, M, N, K, dtype, epilogue, out, ldo, gamma,
                      static_cast<cudaStream_t>(stream), &ln);
@@ -136,12 +195,12 @@ extern "C" int vtq_gemm_ln_slots(int N) { return N >= 64 ? gemm_ln_slots(N) : 0;
 
 extern "C" int vtq_attention_fwd(vtq_ctx* ctx, const void* qkv, void* out, int n_seq, int S, int heads, int dtype,
                                  int q_rows, void* stream) {
-  if (!ctx) return VTQ_ERR_INVALID;
+  VTQ_ENTER(ctx);
   return launch_attention(ctx, qkv, out, n_seq, S, heads, dtype, q_rows, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int vtq_attention_fwd_trace(vtq_ctx* ctx, const void* qkv, void* out, int n_seq, int S, int heads,
                                        int dtype, long long* trace, void* stream) {
-  if (!ctx) return VTQ_ERR_INVALID;
+  VTQ_ENTER(ctx);
   return launch_attention(ctx, qkv, out, n_seq, S, heads, dtype, 0, static_cast<cudaStream_t>(stream), trace);
 }

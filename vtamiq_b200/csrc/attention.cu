@@ -440,24 +440,13 @@ int launch_attention(vtq_ctx* ctx, const void* qkv, void* out, int n_seq, int S,
   dim3 grid(static_cast<unsigned>(n_items < ctx->num_sms ? n_items : ctx->num_sms));
   // q|k|v rows are dead after this kernel: let them leave L2 first (keeps the residual stream resident)
   const uint64_t hint_qkv = l2_hints_enabled() ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
-  static bool configured[2] = {false, false};
   if (dtype == VTQ_F16) {
-    if (!configured[0]) {
-      cudaError_t e = cudaFuncSetAttribute(attention_kernel<DT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           ATT_SMEM_BYTES);
-      if (e != cudaSuccess) return check_cuda(ctx, e, "attention: cudaFuncSetAttribute");
-      configured[0] = true;
-    }
+    if (int rc = ensure_dyn_smem(ctx, attention_kernel<DT_F16>, ATT_SMEM_BYTES, "attention: cudaFuncSetAttribute")) return rc;
     cudaError_t le = launch_pdl(attention_kernel<DT_F16>, grid, dim3(ATT_THREADS), ATT_SMEM_BYTES, st, tmQKV, tmO, S,
                                 heads, n_seq, q_rows, hint_qkv, trace);
     if (le != cudaSuccess) return check_cuda(ctx, le, "attention launch");
   } else {
-    if (!configured[1]) {
-      cudaError_t e = cudaFuncSetAttribute(attention_kernel<DT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           ATT_SMEM_BYTES);
-      if (e != cudaSuccess) return check_cuda(ctx, e, "attention: cudaFuncSetAttribute");
-      configured[1] = true;
-    }
+    if (int rc = ensure_dyn_smem(ctx, attention_kernel<DT_BF16>, ATT_SMEM_BYTES, "attention: cudaFuncSetAttribute")) return rc;
     cudaError_t le = launch_pdl(attention_kernel<DT_BF16>, grid, dim3(ATT_THREADS), ATT_SMEM_BYTES, st, tmQKV, tmO, S,
                                 heads, n_seq, q_rows, hint_qkv, trace);
     if (le != cudaSuccess) return check_cuda(ctx, le, "attention launch");

@@ -29,6 +29,8 @@ struct DenseLayer {
   const float* gate;       // [B][out_dim] or null
   const float* pre_param;  // PReLU slope applied to the input, or null
   const float* epi_param;  // PReLU slope applied to the output, or null
+  float* aux;              // training: GATE -> the sigmoid gate, PRELU -> the pre-activation; null at inference
+  const float* row_scale;  // training: ADD -> per-pair scale of the branch (DropPath mask / keep_prob); or null
   int in_dim, out_dim, pre, epi;
 };
 struct LayerList {
@@ -186,10 +188,15 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1)
                 const size_t oi = static_cast<size_t>(b0 + lane) * out_dim + ch;
                 float v = (h ? rb[0] : ra[0]) + __ldg(ly.bias + ch);
                 if (ly.epi == DEPI_RELU) v = fmaxf(v, 0.f);
-                else if (ly.epi == DEPI_ADD) v = __ldcg(ly.res + oi) + v;
-                else if (ly.epi == DEPI_GATE)
-                  v = __ldcg(ly.res + oi) + __ldcg(ly.gate + oi) * (1.0f / (1.0f + expf(-v)));
-                else if (ly.epi == DEPI_PRELU) {
+                else if (ly.epi == DEPI_ADD) {
+                  if (ly.row_scale != nullptr) v *= __ldg(ly.row_scale + b0 + lane);
+                  v = __ldcg(ly.res + oi) + v;
+                } else if (ly.epi == DEPI_GATE) {
+                  const float sg = 1.0f / (1.0f + expf(-v));
+                  if (ly.aux != nullptr) ly.aux[oi] = sg;
+                  v = __ldcg(ly.res + oi) + __ldcg(ly.gate + oi) * sg;
+                } else if (ly.epi == DEPI_PRELU) {
+                  if (ly.aux != nullptr) ly.aux[oi] = v;
                   const float a = __ldg(ly.epi_param);
                   v = v > 0.f ? v : a * v;
                 }
@@ -214,20 +221,27 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1)
 
 }  // namespace vtq
 
-using namespace vtq;
+namespace vtq {
 
-extern "C" int64_t vtq_workspace_bytes(const vtq_ctx* ctx, int B, int hidden) {
-  (void)ctx;
-  if (B < 0 || hidden < 0) return 0;
-  // 32 KB of barrier counters, then x, y, g (hidden wide) + one hidden-wide scratch for squeeze / head activations
-  return 32768 + static_cast<int64_t>(4) * B * hidden * static_cast<int64_t>(sizeof(float));
+// Offsets (in floats) of the activations the training forward keeps for the backward pass; see tail_train.cu.
+TailSaved tail_saved_layout(int B, int num_rgs, int num_rcabs, int hidden, int ca_hidden, int head_hidden) {
+  TailSaved t;
+  size_t o = 0;
+  const size_t bh = static_cast<size_t>(B) * hidden;
+  t.d = o; o += bh;
+  t.rcab0 = o;
+  t.rcab_stride = 3 * bh + static_cast<size_t>(B) * ca_hidden;   // y, sg, xo (hidden wide) + hc (ca_hidden wide)
+  t.group_stride = static_cast<size_t>(num_rcabs) * t.rcab_stride + bh;  // + gout
+  o += static_cast<size_t>(num_rgs) * t.group_stride;
+  t.z = o; o += (num_rgs > 0 ? bh : 0);
+  t.u = o; o += static_cast<size_t>(B) * head_hidden;
+  t.hh = o; o += static_cast<size_t>(B) * head_hidden;
+  t.total = o;
+  return t;
 }
 
-extern "C" int vtq_diffnet_head(vtq_ctx* ctx, const float* diff, const void* const* params, int n_params,
-                                int num_rgs, int num_rcabs, int hidden, int ca_hidden, int head_hidden, int B,
-                                float* q, void* workspace, void* stream) {
-  if (!ctx) return VTQ_ERR_INVALID;
-  VTQ_CHECK_ARG(ctx, diff && params && q && workspace, "null pointer");
+int check_tail_args(vtq_ctx* ctx, const void* const* params, int n_params, int num_rgs, int num_rcabs,
+                           int hidden, int ca_hidden, int head_hidden, int B) {
   VTQ_CHECK_ARG(ctx, B >= 1 && hidden % 4 == 0 && hidden <= 128 * DENSE_KV && head_hidden % 4 == 0 && head_hidden >= 4,
                 "shape (hidden must be a multiple of 4, <= 1024)");
   VTQ_CHECK_ARG(ctx, num_rgs == 0 || (ca_hidden % 4 == 0 && ca_hidden >= 4),
@@ -244,64 +258,19 @@ extern "C" int vtq_diffnet_head(vtq_ctx* ctx, const float* diff, const void* con
     const bool final_conv = (i == num_rgs * (num_rcabs * 7 + 2) || i == num_rgs * (num_rcabs * 7 + 2) + 1);
     VTQ_CHECK_ARG(ctx, params[i] != nullptr || (final_conv && num_rgs == 0), "null parameter");
   }
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t plane = static_cast<size_t>(B) * hidden;
-  unsigned* counters = static_cast<unsigned*>(workspace);        // first 32 KB: barrier counters
-  float* xbuf = reinterpret_cast<float*>(static_cast<char*>(workspace) + 32768);
-  float* ybuf = xbuf + plane;
-  float* gbuf = ybuf + plane;
-  float* hbuf = gbuf + plane;
-  auto P = [&](int i) { return static_cast<const float*>(params[i]); };
+  return VTQ_OK;
+}
 
-  LayerList L;
-  L.n = 0;
-  auto add = [&](const float* in, int in_dim, const float* W, const float* bias, int out_dim, int pre,
-                 const float* pre_param, int epi, float* out, const float* res, const float* gate,
-                 const float* epi_param) {
-    DenseLayer& d = L.l[L.n++];
-    d.W = W; d.bias = bias; d.in = in; d.out = out; d.res = res; d.gate = gate;
-    d.pre_param = pre_param; d.epi_param = epi_param;
-    d.in_dim = in_dim; d.out_dim = out_dim; d.pre = pre; d.epi = epi;
-  };
-  int pi = 0;
-  const float* g_in = diff;  // group input (skip source)
-  for (int g = 0; g < num_rgs; ++g) {
-    const float* x_in = g_in;
-    for (int r = 0; r < num_rcabs; ++r) {
-      const float *a = P(pi), *W1 = P(pi + 1), *b1 = P(pi + 2), *Wd = P(pi + 3), *bd = P(pi + 4), *Wu = P(pi + 5),
-                  *bu = P(pi + 6);
-      pi += 7;
-      add(x_in, hidden, W1, b1, hidden, PRE_PRELU, a, DEPI_NONE, ybuf, nullptr, nullptr, nullptr);
-      add(ybuf, hidden, Wd, bd, ca_hidden, PRE_NONE, nullptr, DEPI_RELU, hbuf, nullptr, nullptr, nullptr);
-      add(hbuf, ca_hidden, Wu, bu, hidden, PRE_NONE, nullptr, DEPI_GATE, xbuf, x_in, ybuf, nullptr);
-      x_in = xbuf;
-    }
-    add(x_in, hidden, P(pi), P(pi + 1), hidden, PRE_NONE, nullptr, DEPI_ADD, gbuf, g_in, nullptr, nullptr);
-    pi += 2;
-    g_in = gbuf;
-  }
-  const float* z = g_in;
-  if (num_rgs > 0) {
-    add(g_in, hidden, P(pi), P(pi + 1), hidden, PRE_NONE, nullptr, DEPI_NONE, ybuf, nullptr, nullptr, nullptr);
-    z = ybuf;
-  }
-  pi += 2;
-  add(z, hidden, P(pi), P(pi + 1), head_hidden, PRE_NONE, nullptr, DEPI_PRELU, hbuf, nullptr, nullptr, P(pi + 2));
-  add(hbuf, head_hidden, P(pi + 3), P(pi + 4), 1, PRE_NONE, nullptr, DEPI_NONE, q, nullptr, nullptr, nullptr);
-
-  // grid: T columns of G CTAs, all co-resident (cooperative launch): G*T <= #SMs
+// Launch the fused decoder on a prepared layer list (cooperative grid: T columns of G CTAs, all co-resident).
+static int launch_layer_list(vtq_ctx* ctx, const LayerList& L, int B, int hidden, unsigned* counters, cudaStream_t st) {
+  const int smem = (DENSE_PAIRS + DENSE_WROWS) * hidden * static_cast<int>(sizeof(float));
   const int n_tiles = (B + DENSE_PAIRS - 1) / DENSE_PAIRS;
   int T = n_tiles < 8 ? n_tiles : 8;
   int G = ctx->num_sms / T;
   if (G > 96) G = 96;
   if (G < 1) G = 1;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(diffnet_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         ctx->smem_optin < 200 * 1024 ? ctx->smem_optin : 200 * 1024);
-    if (e != cudaSuccess) return check_cuda(ctx, e, "diffnet: cudaFuncSetAttribute");
-    configured = true;
-  }
+  if (int rc = ensure_dyn_smem(ctx, diffnet_fused_kernel, ctx->smem_optin < 200 * 1024 ? ctx->smem_optin : 200 * 1024,
+                               "diffnet: cudaFuncSetAttribute")) return rc;
   cudaError_t e = cudaMemsetAsync(counters, 0, 32768, st);
   if (e != cudaSuccess) return check_cuda(ctx, e, "diffnet: cudaMemsetAsync");
   cudaLaunchConfig_t cfg = {};
@@ -318,4 +287,122 @@ extern "C" int vtq_diffnet_head(vtq_ctx* ctx, const float* diff, const void* con
   if (e != cudaSuccess) return check_cuda(ctx, e, "diffnet: cooperative launch");
   VTQ_CHECK_LAUNCH(ctx, "diffnet fused launch");
   return VTQ_OK;
+}
+
+static void add_layer(LayerList& L, const float* in, int in_dim, const float* W, const float* bias, int out_dim,
+                      int pre, const float* pre_param, int epi, float* out, const float* res, const float* gate,
+                      const float* epi_param, float* aux = nullptr, const float* row_scale = nullptr) {
+  DenseLayer& d = L.l[L.n++];
+  d.W = W; d.bias = bias; d.in = in; d.out = out; d.res = res; d.gate = gate;
+  d.pre_param = pre_param; d.epi_param = epi_param; d.aux = aux; d.row_scale = row_scale;
+  d.in_dim = in_dim; d.out_dim = out_dim; d.pre = pre; d.epi = epi;
+}
+
+// Training forward of the tail: the same fused decoder, but every activation the backward pass needs lands in its own
+// slot of `saved` (tail_saved_layout) instead of four rotating buffers; the sigmoid gates and the head's
+// pre-activation are kept (aux), and DropPath scales the residual-group branches per pair (drop_scale).
+int launch_tail_train_forward(vtq_ctx* ctx, const float* d_scaled_in_saved, const void* const* params, int n_params,
+                              int num_rgs, int num_rcabs, int hidden, int ca_hidden, int head_hidden, int B,
+                              const float* drop_scale, float* saved, float* q, unsigned* counters, cudaStream_t st) {
+  (void)n_params;
+  const TailSaved t = tail_saved_layout(B, num_rgs, num_rcabs, hidden, ca_hidden, head_hidden);
+  const size_t bh = static_cast<size_t>(B) * hidden;
+  auto P = [&](int i) { return static_cast<const float*>(params[i]); };
+  LayerList L;
+  L.n = 0;
+  int pi = 0;
+  const float* g_in = d_scaled_in_saved;
+  for (int g = 0; g < num_rgs; ++g) {
+    float* gbase = saved + t.rcab0 + static_cast<size_t>(g) * t.group_stride;
+    const float* x_in = g_in;
+    for (int r = 0; r < num_rcabs; ++r) {
+      float* y = gbase + static_cast<size_t>(r) * t.rcab_stride;
+      float* sg = y + bh;
+      float* xo = sg + bh;
+      float* hc = xo + bh;
+      const float *a = P(pi), *W1 = P(pi + 1), *b1 = P(pi + 2), *Wd = P(pi + 3), *bd = P(pi + 4), *Wu = P(pi + 5),
+                  *bu = P(pi + 6);
+      pi += 7;
+      add_layer(L, x_in, hidden, W1, b1, hidden, PRE_PRELU, a, DEPI_NONE, y, nullptr, nullptr, nullptr);
+      add_layer(L, y, hidden, Wd, bd, ca_hidden, PRE_NONE, nullptr, DEPI_RELU, hc, nullptr, nullptr, nullptr);
+      add_layer(L, hc, ca_hidden, Wu, bu, hidden, PRE_NONE, nullptr, DEPI_GATE, xo, x_in, y, nullptr, sg);
+      x_in = xo;
+    }
+    float* gout = gbase + static_cast<size_t>(num_rcabs) * t.rcab_stride;
+    add_layer(L, x_in, hidden, P(pi), P(pi + 1), hidden, PRE_NONE, nullptr, DEPI_ADD, gout, g_in, nullptr, nullptr,
+              nullptr, drop_scale ? drop_scale + static_cast<size_t>(g) * B : nullptr);
+    pi += 2;
+    g_in = gout;
+  }
+  const float* z = g_in;
+  if (num_rgs > 0) {
+    add_layer(L, g_in, hidden, P(pi), P(pi + 1), hidden, PRE_NONE, nullptr, DEPI_NONE, saved + t.z, nullptr, nullptr,
+              nullptr);
+    z = saved + t.z;
+  }
+  pi += 2;
+  add_layer(L, z, hidden, P(pi), P(pi + 1), head_hidden, PRE_NONE, nullptr, DEPI_PRELU, saved + t.hh, nullptr, nullptr,
+            P(pi + 2), saved + t.u);
+  add_layer(L, saved + t.hh, head_hidden, P(pi + 3), P(pi + 4), 1, PRE_NONE, nullptr, DEPI_NONE, q, nullptr, nullptr,
+            nullptr);
+  return launch_layer_list(ctx, L, B, hidden, counters, st);
+}
+
+}  // namespace vtq
+
+using namespace vtq;
+
+extern "C" int64_t vtq_workspace_bytes(const vtq_ctx* ctx, int B, int hidden) {
+  (void)ctx;
+  if (B < 0 || hidden < 0) return 0;
+  // 32 KB of barrier counters, then x, y, g (hidden wide) + one hidden-wide scratch for squeeze / head activations
+  return 32768 + static_cast<int64_t>(4) * B * hidden * static_cast<int64_t>(sizeof(float));
+}
+
+extern "C" int vtq_diffnet_head(vtq_ctx* ctx, const float* diff, const void* const* params, int n_params,
+                                int num_rgs, int num_rcabs, int hidden, int ca_hidden, int head_hidden, int B,
+                                float* q, void* workspace, void* stream) {
+  VTQ_ENTER(ctx);
+  VTQ_CHECK_ARG(ctx, diff && params && q && workspace, "null pointer");
+  if (int rc = check_tail_args(ctx, params, n_params, num_rgs, num_rcabs, hidden, ca_hidden, head_hidden, B)) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t plane = static_cast<size_t>(B) * hidden;
+  unsigned* counters = static_cast<unsigned*>(workspace);        // first 32 KB: barrier counters
+  float* xbuf = reinterpret_cast<float*>(static_cast<char*>(workspace) + 32768);
+  float* ybuf = xbuf + plane;
+  float* gbuf = ybuf + plane;
+  float* hbuf = gbuf + plane;
+  auto P = [&](int i) { return static_cast<const float*>(params[i]); };
+
+  LayerList L;
+  L.n = 0;
+  int pi = 0;
+  const float* g_in = diff;  // group input (skip source)
+  for (int g = 0; g < num_rgs; ++g) {
+    const float* x_in = g_in;
+    for (int r = 0; r < num_rcabs; ++r) {
+      const float *a = P(pi), *W1 = P(pi + 1), *b1 = P(pi + 2), *Wd = P(pi + 3), *bd = P(pi + 4), *Wu = P(pi + 5),
+                  *bu = P(pi + 6);
+      pi += 7;
+      add_layer(L, x_in, hidden, W1, b1, hidden, PRE_PRELU, a, DEPI_NONE, ybuf, nullptr, nullptr, nullptr);
+      add_layer(L, ybuf, hidden, Wd, bd, ca_hidden, PRE_NONE, nullptr, DEPI_RELU, hbuf, nullptr, nullptr, nullptr);
+      add_layer(L, hbuf, ca_hidden, Wu, bu, hidden, PRE_NONE, nullptr, DEPI_GATE, xbuf, x_in, ybuf, nullptr);
+      x_in = xbuf;
+    }
+    // NOTE: the group conv reads x_in (= xbuf) and writes gbuf while its skip source g_in may BE gbuf (groups >= 1):
+    // each output element reads res[oi] and writes out[oi] at the same index in the same thread, so that is safe.
+    add_layer(L, x_in, hidden, P(pi), P(pi + 1), hidden, PRE_NONE, nullptr, DEPI_ADD, gbuf, g_in, nullptr, nullptr);
+    pi += 2;
+    g_in = gbuf;
+  }
+  const float* z = g_in;
+  if (num_rgs > 0) {
+    add_layer(L, g_in, hidden, P(pi), P(pi + 1), hidden, PRE_NONE, nullptr, DEPI_NONE, ybuf, nullptr, nullptr, nullptr);
+    z = ybuf;
+  }
+  pi += 2;
+  add_layer(L, z, hidden, P(pi), P(pi + 1), head_hidden, PRE_NONE, nullptr, DEPI_PRELU, hbuf, nullptr, nullptr,
+            P(pi + 2));
+  add_layer(L, hbuf, head_hidden, P(pi + 3), P(pi + 4), 1, PRE_NONE, nullptr, DEPI_NONE, q, nullptr, nullptr, nullptr);
+  return launch_layer_list(ctx, L, B, hidden, counters, st);
 }

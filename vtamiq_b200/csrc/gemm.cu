@@ -682,12 +682,7 @@ static int launch_1cta(vtq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& 
                        uint64_t hint_a, uint64_t hint_o, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_kernel<DT, BN, EPI, GELU>;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return check_cuda(ctx, e, "gemm: cudaFuncSetAttribute");
-    configured = true;
-  }
+  if (int rc = ensure_dyn_smem(ctx, kern, Cfg::SMEM_BYTES, "gemm: cudaFuncSetAttribute")) return rc;
   const int num_tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
   const int grid = num_tiles < ctx->num_sms ? num_tiles : ctx->num_sms;
   cudaError_t le = launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, st, tmA, tmB, tmO, bias, gamma, M,
@@ -703,12 +698,7 @@ static int launch_2cta(vtq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& 
                        int accumulate, uint64_t hint_a, uint64_t hint_o, const LnFold& ln, cudaStream_t st) {
   using Cfg = Gemm2Cfg<BN, LN>;
   auto kern = gemm2_kernel<DT, BN, EPI, GELU, LN>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return check_cuda(ctx, e, "gemm2: cudaFuncSetAttribute");
-    configured = true;
-  }
+  if (int rc = ensure_dyn_smem(ctx, kern, Cfg::SMEM_BYTES, "gemm2: cudaFuncSetAttribute")) return rc;
   const int num_tiles = ((M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * ((N + BN - 1) / BN);
   const int max_pairs = ctx->num_sms / 2;
   const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;

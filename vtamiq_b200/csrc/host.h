@@ -6,7 +6,10 @@
 #include <stdint.h>
 
 #include <cstdlib>
+#include <cstring>
 #include <string>
+#include <unordered_map>
+#include <unordered_set>
 
 #include "../../include/vtamiq_b200.h"
 
@@ -20,12 +23,49 @@ struct vtq_ctx {
                            CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
   std::string last_error;
   unsigned long long launches = 0;  // kernels launched through this handle (bench.py reports it)
+  // Per-DEVICE state (one handle per device): kernels whose dynamic shared-memory opt-in has been raised on this
+  // device (cudaFuncSetAttribute is per device, not per process), and the encoded TMA descriptors keyed by their
+  // full encoding arguments (base pointer, shape, strides, box, type, swizzle): steady-state launches re-use them.
+  std::unordered_set<const void*> smem_configured;
+  std::unordered_map<std::string, CUtensorMap> tensor_maps;
+  unsigned long long tensor_map_hits = 0, tensor_map_misses = 0;
+  int* oob_flag_host = nullptr;  // pinned + mapped: gather kernels set it when a coordinate is out of range
+  int* oob_flag_dev = nullptr;
 };
 
 namespace vtq {
 
 int fail(vtq_ctx* ctx, int code, const std::string& msg);
 int check_cuda(vtq_ctx* ctx, cudaError_t e, const char* what);
+
+// Raise a kernel's dynamic shared-memory limit once per (device, kernel).
+template <typename K>
+int ensure_dyn_smem(vtq_ctx* ctx, K kern, int bytes, const char* what) {
+  const void* key = reinterpret_cast<const void*>(kern);
+  if (ctx->smem_configured.count(key)) return VTQ_OK;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return check_cuda(ctx, e, what);
+  ctx->smem_configured.insert(key);
+  return VTQ_OK;
+}
+
+// Every entry point runs on the handle's device whatever the caller's current device is, and leaves the caller's
+// current device untouched.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(const vtq_ctx* ctx) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != ctx->device) switched = cudaSetDevice(ctx->device) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define VTQ_ENTER(ctx)                     \
+  if (!(ctx)) return VTQ_ERR_INVALID;      \
+  ::vtq::DeviceGuard vtq_device_guard__(ctx)
 
 // dims/strides innermost-first; strides in BYTES for dims 1..rank-1; all tiles use 128B swizzle.
 int make_tensor_map(vtq_ctx* ctx, CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base,
@@ -83,6 +123,23 @@ int gemm_ln_slots(int N);
 int launch_gemm(vtq_ctx* ctx, const void* A, int64_t lda, const void* W, const float* bias, int M, int N, int K,
                 int dtype, int epilogue, void* out, int64_t ldo, const float* gamma, cudaStream_t st,
                 const GemmLnArgs* lnargs = nullptr);
+// Slots (offsets in floats) of the activations the training forward of the tail keeps for its backward pass.
+struct TailSaved {
+  size_t d;             // gamma * d0                                   [B][hidden]
+  size_t rcab0;         // first RCAB record; RCAB (g, r) at rcab0 + g*group_stride + r*rcab_stride:
+  size_t rcab_stride;   //   y [B][hidden], sg (sigmoid gate) [B][hidden], xo (block output) [B][hidden], hc [B][ca]
+  size_t group_stride;  //   ... followed, per group, by gout [B][hidden]
+  size_t z;             // final conv output                           [B][hidden]   (num_rgs > 0)
+  size_t u;             // head hidden pre-activation                  [B][head_hidden]
+  size_t hh;            // head hidden after PReLU                     [B][head_hidden]
+  size_t total;
+};
+int check_tail_args(vtq_ctx* ctx, const void* const* params, int n_params, int num_rgs, int num_rcabs, int hidden,
+                    int ca_hidden, int head_hidden, int B);
+TailSaved tail_saved_layout(int B, int num_rgs, int num_rcabs, int hidden, int ca_hidden, int head_hidden);
+int launch_tail_train_forward(vtq_ctx* ctx, const float* d_scaled_in_saved, const void* const* params, int n_params,
+                              int num_rgs, int num_rcabs, int hidden, int ca_hidden, int head_hidden, int B,
+                              const float* drop_scale, float* saved, float* q, unsigned* counters, cudaStream_t st);
 int launch_attention(vtq_ctx* ctx, const void* qkv, void* out, int n_seq, int S, int heads, int dtype,
                      int q_rows, cudaStream_t st, long long* trace = nullptr);
 

@@ -1,149 +1,10 @@
-// HBM-bound kernels of the path: K1 patch gather (+uv, scale ids), 2x2 mean pyramid, fp32->16-bit cast,
-// K2 embedding assembly, K4 LayerNorm, K7 quality-token LayerNorm + difference.
+// HBM-bound row kernels of the path: fp32->16-bit cast, K2 embedding assembly, K4 LayerNorm, K7 quality-token
+// LayerNorm + difference.  (K1 — patch gather, pyramid, uint8 transform — lives in gather.cu.)
 // All are one-pass, coalesced, 128-bit on the wide side; none has data reuse worth staging in smem.
 #include "common.cuh"
 #include "host.h"
 
 namespace vtq {
-
-constexpr int PATCH = 16;
-constexpr int PATCH_ELEMS = 3 * PATCH * PATCH;  // 768
-
-// ------------------------------------------------------------------------------------------------
-// K1: patch gather.  grid = (n patches, n_img); 192 threads, each moves 4 horizontally adjacent pixels:
-// 4 scalar loads (source x0 is only 4-byte aligned), one 128-bit fp32 store and/or one 64-bit 16-bit store.
-// Thread 0 also emits uv and the scale id.  Reference semantics: data/patch_sampling.py:529-545,:559-568.
-// ------------------------------------------------------------------------------------------------
-template <int DT>
-__global__ void __launch_bounds__(192) patch_gather_kernel(const float* __restrict__ images, int H, int W,
-                                                           const double* __restrict__ samples, int n_set, int n,
-                                                           int patch_offset, int N_total,
-                                                           float* __restrict__ patches_f32,
-                                                           void* __restrict__ patches_16, float* __restrict__ pos,
-                                                           float* __restrict__ scales, float scale_id) {
-  const int p = blockIdx.x;
-  const int img = blockIdx.y;
-  const int set = img % n_set;
-  const double sy = samples[(static_cast<size_t>(set) * 2 + 0) * n + p];
-  const double sx = samples[(static_cast<size_t>(set) * 2 + 1) * n + p];
-  // torch advanced indexing with float64 indices truncates toward zero; coords are >= 0
-  const int y0 = static_cast<int>(sy);
-  const int x0 = static_cast<int>(sx);
-  const size_t slot = static_cast<size_t>(img) * N_total + patch_offset + p;
-
-  const int t = threadIdx.x;       // 0..191: (c, i, j4)
-  const int c = t >> 6;            // channel
-  const int i = (t >> 2) & 15;     // row inside the patch
-  const int j4 = (t & 3) * 4;      // first of 4 columns
-  const float* src = images + ((static_cast<size_t>(img) * 3 + c) * H + (y0 + i)) * W + x0 + j4;
-  const float v0 = __ldg(src + 0), v1 = __ldg(src + 1), v2 = __ldg(src + 2), v3 = __ldg(src + 3);
-  const size_t o = slot * PATCH_ELEMS + static_cast<size_t>(t) * 4;
-  if (patches_f32 != nullptr) *reinterpret_cast<float4*>(patches_f32 + o) = make_float4(v0, v1, v2, v3);
-  if (patches_16 != nullptr) {
-    uint2 h = make_uint2(pack2<DT>(v0, v1), pack2<DT>(v2, v3));
-    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(patches_16) + o) = h;
-  }
-  if (t == 0) {
-    if (pos != nullptr) {
-      // (sample + P/2) / (dim - P/2) in float64, clamp to [0, 1 - 1e-6], round once to fp32 on store
-      const double hi = 1.0 - 1e-6;
-      double u = (sy + 8.0) / static_cast<double>(static_cast<float>(H - 8));
-      double v = (sx + 8.0) / static_cast<double>(static_cast<float>(W - 8));
-      u = fmin(fmax(u, 0.0), hi);
-      v = fmin(fmax(v, 0.0), hi);
-      pos[slot * 2 + 0] = __double2float_rn(u);
-      pos[slot * 2 + 1] = __double2float_rn(v);
-    }
-    if (scales != nullptr) scales[slot] = scale_id;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K1 (uint8 source): the reference decodes to uint8 HWC, then to_tensor (/255) and normalize ((x-.5)/.5)
-// (data/utils.py:76,:94; patch_datasets.py:51-52) before gathering.  Fusing that transform into the gather keeps
-// the images in HBM as uint8 (4x fewer bytes) and never materialises the fp32 image; the three fp32 operations
-// are performed in the reference's order with IEEE-rounded intrinsics, so the patches are bit-identical.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float normalize_u8(uint8_t u) {
-  return __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(u), 255.0f), 0.5f), 0.5f);
-}
-
-template <int DT>
-__global__ void __launch_bounds__(192) patch_gather_u8_kernel(const uint8_t* __restrict__ images, int H, int W,
-                                                              const double* __restrict__ samples, int n_set, int n,
-                                                              int N_total, float* __restrict__ patches_f32,
-                                                              void* __restrict__ patches_16, float* __restrict__ pos) {
-  const int p = blockIdx.x;
-  const int img = blockIdx.y;
-  const int set = img % n_set;
-  const double sy = samples[(static_cast<size_t>(set) * 2 + 0) * n + p];
-  const double sx = samples[(static_cast<size_t>(set) * 2 + 1) * n + p];
-  const int y0 = static_cast<int>(sy);
-  const int x0 = static_cast<int>(sx);
-  const size_t slot = static_cast<size_t>(img) * N_total + p;
-  const int t = threadIdx.x;    // (c, i, j4)
-  const int c = t >> 6;
-  const int i = (t >> 2) & 15;
-  const int j4 = (t & 3) * 4;
-  const uint8_t* src = images + ((static_cast<size_t>(img) * H + (y0 + i)) * W + x0 + j4) * 3 + c;  // HWC
-  const float v0 = normalize_u8(__ldg(src)), v1 = normalize_u8(__ldg(src + 3)), v2 = normalize_u8(__ldg(src + 6)),
-              v3 = normalize_u8(__ldg(src + 9));
-  const size_t o = slot * PATCH_ELEMS + static_cast<size_t>(t) * 4;
-  if (patches_f32 != nullptr) *reinterpret_cast<float4*>(patches_f32 + o) = make_float4(v0, v1, v2, v3);
-  if (patches_16 != nullptr)
-    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(patches_16) + o) = make_uint2(pack2<DT>(v0, v1), pack2<DT>(v2, v3));
-  if (t == 0 && pos != nullptr) {
-    const double hi = 1.0 - 1e-6;
-    double u = (sy + 8.0) / static_cast<double>(static_cast<float>(H - 8));
-    double v = (sx + 8.0) / static_cast<double>(static_cast<float>(W - 8));
-    pos[slot * 2 + 0] = __double2float_rn(fmin(fmax(u, 0.0), hi));
-    pos[slot * 2 + 1] = __double2float_rn(fmin(fmax(v, 0.0), hi));
-  }
-}
-
-// uint8 HWC -> normalised fp32 CHW (needed only in front of the pyramid for multi-scale sampling)
-__global__ void normalize_u8_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, int H, int W,
-                                    size_t total) {
-  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;  // over [img][c][y][x]
-  if (idx >= total) return;
-  const int x = static_cast<int>(idx % W);
-  size_t rem = idx / W;
-  const int y = static_cast<int>(rem % H);
-  rem /= H;
-  const int c = static_cast<int>(rem % 3);
-  const size_t img = rem / 3;
-  dst[idx] = normalize_u8(__ldg(src + ((img * H + y) * W + x) * 3 + c));
-}
-
-// ------------------------------------------------------------------------------------------------
-// 2x2 mean, floor mode; the summation tree and the exact /4 follow ATen's avg_pool2d (kh outer, kw inner).
-// ------------------------------------------------------------------------------------------------
-__global__ void avgpool2x2_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int W, int Ho,
-                                  int Wo, size_t total) {
-  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  if (idx >= total) return;
-  const int xo = static_cast<int>(idx % Wo);
-  const size_t rem = idx / Wo;
-  const int yo = static_cast<int>(rem % Ho);
-  const size_t plane = rem / Ho;
-  const float* s = src + (plane * H + 2 * yo) * static_cast<size_t>(W) + 2 * xo;
-  const float2 a = *reinterpret_cast<const float2*>(s);  // 2*xo even, W arbitrary: alignment handled below
-  const float2 b = *reinterpret_cast<const float2*>(s + W);
-  dst[idx] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(a.x, a.y), b.x), b.y), 0.25f);
-}
-
-__global__ void avgpool2x2_kernel_unaligned(const float* __restrict__ src, float* __restrict__ dst, int H, int W,
-                                            int Ho, int Wo, size_t total) {
-  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  if (idx >= total) return;
-  const int xo = static_cast<int>(idx % Wo);
-  const size_t rem = idx / Wo;
-  const int yo = static_cast<int>(rem % Ho);
-  const size_t plane = rem / Ho;
-  const float* s = src + (plane * H + 2 * yo) * static_cast<size_t>(W) + 2 * xo;
-  dst[idx] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(__ldg(s), __ldg(s + 1)), __ldg(s + W)), __ldg(s + W + 1)),
-                       0.25f);
-}
 
 // ------------------------------------------------------------------------------------------------
 // fp32 -> 16-bit, 8 elements per thread (2 x 128-bit loads, 1 x 128-bit store)
@@ -199,8 +60,12 @@ __global__ void __launch_bounds__(256) embed_assemble_kernel(
     const float fu = floorf(__fmul_rn(pos[pr * 2 + 0], g));
     const float fv = floorf(__fmul_rn(pos[pr * 2 + 1], g));
     const float fidx = __fadd_rn(__fadd_rn(__fmul_rn(fu, g), fv), 1.0f);
-    const long long idx = static_cast<long long>(fidx);
-    if (lane == 0 && pos_idx != nullptr) pos_idx[pr] = static_cast<int32_t>(idx);
+    // uv outside [0, 1) (or NaN) would index outside the table — the reference raises IndexError there.  The row
+    // index is clamped to the table (memory-safe); the dump keeps the UNclamped value so a caller can detect it.
+    const long long raw_idx = static_cast<long long>(fidx);
+    const long long last = static_cast<long long>(grid_w) * grid_w;
+    const long long idx = raw_idx < 0 ? 0 : (raw_idx > last ? last : raw_idx);
+    if (lane == 0 && pos_idx != nullptr) pos_idx[pr] = static_cast<int32_t>(raw_idx);
     ptab = pos_table + static_cast<size_t>(idx) * hidden;
   }
   if (scale_table != nullptr) {
@@ -371,51 +236,9 @@ __global__ void __launch_bounds__(128) cls_diff_kernel(const float* __restrict__
 // ================================================================================================
 using namespace vtq;
 
-extern "C" int vtq_patch_gather(vtq_ctx* ctx, const float* images, int n_img, int H, int W, const double* samples,
-                                int n_set, int n, int patch_offset, int N_total, float* patches_f32,
-                                void* patches_16, int dtype, float* pos, float* scales, int scale_id,
-                                void* stream) {
-  if (!ctx) return VTQ_ERR_INVALID;
-  VTQ_CHECK_ARG(ctx, images && samples, "null pointer");
-  VTQ_CHECK_ARG(ctx, H >= PATCH && W >= PATCH, "image smaller than one patch");
-  VTQ_CHECK_ARG(ctx, n_img >= 1 && n_set >= 1 && n_img % n_set == 0, "n_img must be a multiple of n_set");
-  VTQ_CHECK_ARG(ctx, n >= 0 && patch_offset >= 0 && patch_offset + n <= N_total, "patch range");
-  VTQ_CHECK_ARG(ctx, n_img <= 65535, "n_img <= 65535");
-  VTQ_CHECK_ARG(ctx, dtype == VTQ_F16 || dtype == VTQ_BF16, "dtype");
-  if (n == 0) return VTQ_OK;
-  dim3 grid(n, n_img);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == VTQ_F16)
-    patch_gather_kernel<DT_F16><<<grid, 192, 0, st>>>(images, H, W, samples, n_set, n, patch_offset, N_total,
-                                                      patches_f32, patches_16, pos, scales,
-                                                      static_cast<float>(scale_id));
-  else
-    patch_gather_kernel<DT_BF16><<<grid, 192, 0, st>>>(images, H, W, samples, n_set, n, patch_offset, N_total,
-                                                       patches_f32, patches_16, pos, scales,
-                                                       static_cast<float>(scale_id));
-  VTQ_CHECK_LAUNCH(ctx, "patch_gather launch");
-  return VTQ_OK;
-}
-
-extern "C" int vtq_avgpool2x2(vtq_ctx* ctx, const float* src, float* dst, int planes, int H, int W, void* stream) {
-  if (!ctx) return VTQ_ERR_INVALID;
-  VTQ_CHECK_ARG(ctx, src && dst, "null pointer");
-  VTQ_CHECK_ARG(ctx, planes >= 1 && H >= 2 && W >= 2, "shape");
-  const int Ho = H / 2, Wo = W / 2;
-  const size_t total = static_cast<size_t>(planes) * Ho * Wo;
-  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (W % 2 == 0 && reinterpret_cast<uintptr_t>(src) % 8 == 0)
-    avgpool2x2_kernel<<<blocks, 256, 0, st>>>(src, dst, H, W, Ho, Wo, total);
-  else
-    avgpool2x2_kernel_unaligned<<<blocks, 256, 0, st>>>(src, dst, H, W, Ho, Wo, total);
-  VTQ_CHECK_LAUNCH(ctx, "avgpool2x2 launch");
-  return VTQ_OK;
-}
-
 extern "C" int vtq_cast_rows(vtq_ctx* ctx, const float* src, void* dst16, int64_t n_elems, int dtype,
                              void* stream) {
-  if (!ctx) return VTQ_ERR_INVALID;
+  VTQ_ENTER(ctx);
   VTQ_CHECK_ARG(ctx, src && dst16, "null pointer");
   VTQ_CHECK_ARG(ctx, n_elems >= 0 && n_elems % 8 == 0, "element count must be a multiple of 8");
   VTQ_CHECK_ARG(ctx, (reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst16)) % 16 == 0,
@@ -435,7 +258,7 @@ extern "C" int vtq_embed_assemble(vtq_ctx* ctx, const float* proj, const float* 
                                   const float* pos_table, int grid, const float* scale_table, int num_scales,
                                   const float* cls_token, const float* extra_tokens, int n_extra, int n_seq, int N,
                                   int hidden, float* x, int32_t* pos_idx, int32_t* scale_idx, void* stream) {
-  if (!ctx) return VTQ_ERR_INVALID;
+  VTQ_ENTER(ctx);
   VTQ_CHECK_ARG(ctx, proj && x, "null pointer");
   VTQ_CHECK_ARG(ctx, hidden % 4 == 0 && hidden >= 4, "hidden must be a multiple of 4");
   VTQ_CHECK_ARG(ctx, n_seq >= 1 && N >= 1 && n_extra >= 0, "shape");
@@ -455,7 +278,7 @@ extern "C" int vtq_embed_assemble(vtq_ctx* ctx, const float* proj, const float* 
 
 extern "C" int vtq_layernorm(vtq_ctx* ctx, const float* x, int64_t x_stride, const float* weight, const float* bias,
                              float eps, int64_t rows, int hidden, void* out16, int dtype, void* stream) {
-  if (!ctx) return VTQ_ERR_INVALID;
+  VTQ_ENTER(ctx);
   VTQ_CHECK_ARG(ctx, x && weight && bias && out16, "null pointer");
   VTQ_CHECK_ARG(ctx, hidden == 768 || hidden == 1024, "hidden must be 768 or 1024");
   VTQ_CHECK_ARG(ctx, rows >= 0, "rows");
@@ -483,7 +306,7 @@ extern "C" int vtq_layernorm(vtq_ctx* ctx, const float* x, int64_t x_stride, con
 
 extern "C" int vtq_rowstats_cast(vtq_ctx* ctx, const float* x, int64_t rows, int hidden, void* raw16_out,
                                  float* ln_out, int dtype, void* stream) {
-  if (!ctx) return VTQ_ERR_INVALID;
+  VTQ_ENTER(ctx);
   VTQ_CHECK_ARG(ctx, x && raw16_out && ln_out, "null pointer");
   VTQ_CHECK_ARG(ctx, hidden == 768 || hidden == 1024, "hidden must be 768 or 1024");
   VTQ_CHECK_ARG(ctx, rows >= 1, "rows");
@@ -508,7 +331,7 @@ extern "C" int vtq_rowstats_cast(vtq_ctx* ctx, const float* x, int64_t rows, int
 extern "C" int vtq_cls_diff(vtq_ctx* ctx, const float* x_ref, const float* x_dist, int B, int S, int hidden, int token,
                             const float* ln_weight, const float* ln_bias, float eps, const float* gamma,
                             float* diff, void* stream) {
-  if (!ctx) return VTQ_ERR_INVALID;
+  VTQ_ENTER(ctx);
   VTQ_CHECK_ARG(ctx, x_ref && x_dist && ln_weight && ln_bias && diff, "null pointer");
   VTQ_CHECK_ARG(ctx, hidden == 768 || hidden == 1024, "hidden must be 768 or 1024");
   VTQ_CHECK_ARG(ctx, B >= 1 && S >= 1 && token >= 0 && token < S, "shape");
@@ -517,36 +340,5 @@ extern "C" int vtq_cls_diff(vtq_ctx* ctx, const float* x_ref, const float* x_dis
   if (hidden == 768) cls_diff_kernel<6><<<blocks, 128, 0, st>>>(x_ref, x_dist, B, S, token, ln_weight, ln_bias, eps, gamma, diff);
   else cls_diff_kernel<8><<<blocks, 128, 0, st>>>(x_ref, x_dist, B, S, token, ln_weight, ln_bias, eps, gamma, diff);
   VTQ_CHECK_LAUNCH(ctx, "cls_diff launch");
-  return VTQ_OK;
-}
-
-extern "C" int vtq_patch_gather_u8(vtq_ctx* ctx, const uint8_t* images, int n_img, int H, int W,
-                                   const double* samples, int n_set, int n, float* patches_f32, void* patches_16,
-                                   int dtype, float* pos, void* stream) {
-  if (!ctx) return VTQ_ERR_INVALID;
-  VTQ_CHECK_ARG(ctx, images && samples, "null pointer");
-  VTQ_CHECK_ARG(ctx, H >= PATCH && W >= PATCH, "image smaller than one patch");
-  VTQ_CHECK_ARG(ctx, n_img >= 1 && n_set >= 1 && n_img % n_set == 0, "n_img must be a multiple of n_set");
-  VTQ_CHECK_ARG(ctx, n >= 0 && n_img <= 65535, "patch / image count");
-  VTQ_CHECK_ARG(ctx, dtype == VTQ_F16 || dtype == VTQ_BF16, "dtype");
-  if (n == 0) return VTQ_OK;
-  dim3 grid(n, n_img);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == VTQ_F16)
-    patch_gather_u8_kernel<DT_F16><<<grid, 192, 0, st>>>(images, H, W, samples, n_set, n, n, patches_f32, patches_16, pos);
-  else
-    patch_gather_u8_kernel<DT_BF16><<<grid, 192, 0, st>>>(images, H, W, samples, n_set, n, n, patches_f32, patches_16, pos);
-  VTQ_CHECK_LAUNCH(ctx, "patch_gather_u8 launch");
-  return VTQ_OK;
-}
-
-extern "C" int vtq_normalize_u8(vtq_ctx* ctx, const uint8_t* src, float* dst, int n_img, int H, int W, void* stream) {
-  if (!ctx) return VTQ_ERR_INVALID;
-  VTQ_CHECK_ARG(ctx, src && dst, "null pointer");
-  VTQ_CHECK_ARG(ctx, n_img >= 1 && H >= 1 && W >= 1, "shape");
-  const size_t total = static_cast<size_t>(n_img) * 3 * H * W;
-  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
-  normalize_u8_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, H, W, total);
-  VTQ_CHECK_LAUNCH(ctx, "normalize_u8 launch");
   return VTQ_OK;
 }

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+from collections import OrderedDict
 from dataclasses import dataclass
 
 import torch
@@ -26,8 +27,9 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    """The caller's current stream ON `device` (not on whatever device happens to be current)."""
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 @dataclass
@@ -47,12 +49,13 @@ class _LayerPack:
     b_fc2: torch.Tensor
     g2: torch.Tensor | None
     # LayerNorm folded into the consuming GEMM (vtq_gemm_ln): W' = W * ln_w, b' = b + W ln_b, colsum = sum_k W'
-    w_qkv_f: torch.Tensor
-    b_qkv_f: torch.Tensor
-    cs_qkv: torch.Tensor
-    w_fc1_f: torch.Tensor
-    b_fc1_f: torch.Tensor
-    cs_fc1: torch.Tensor
+    # — built only when fuse_layernorm is on
+    w_qkv_f: torch.Tensor | None = None
+    b_qkv_f: torch.Tensor | None = None
+    cs_qkv: torch.Tensor | None = None
+    w_fc1_f: torch.Tensor | None = None
+    b_fc1_f: torch.Tensor | None = None
+    cs_fc1: torch.Tensor | None = None
 
 
 def fold_layernorm(w, b, ln_w, ln_b, dtype16):
@@ -120,7 +123,9 @@ class Engine:
         self.device = None
         self.ctx = None
         self._sig = None
-        self._ws: dict[tuple[int, int], _Workspace] = {}
+        self._ws: "OrderedDict[tuple[int, int, int], _Workspace]" = OrderedDict()
+        self.max_workspaces = int(os.environ.get("VTQ_MAX_WORKSPACES", "4"))   # LRU bound on cached (B, N) workspaces
+        self.static_weights = False   # True: skip the per-forward parameter version walk (weights promised frozen)
         self.dump_indices = False
         self.timeline = None   # when a list: (tag, start_event, end_event) per launch (bench.py roofline leg)
 
@@ -149,7 +154,9 @@ class Engine:
             self.ctx = get_context(p0.device.index if p0.device.index is not None else torch.cuda.current_device())
             self._sig = None
             self._ws.clear()
-        sig = self._signature()
+        if self.static_weights and self._sig is not None:
+            return
+        sig = self._signature() + (self.fuse_layernorm,)
         if sig != self._sig:
             self._pack()
             self._sig = sig
@@ -201,12 +208,16 @@ class Engine:
 
         for L in vit.encoder.layers:
             a = L.attn
-            w_qkv32 = torch.cat([a.query.weight, a.key.weight, a.value.weight], 0)
-            b_qkv32 = torch.cat([a.query.bias, a.key.bias, a.value.bias], 0)
-            w_qkv_f, b_qkv_f, cs_qkv = fold(w_qkv32, b_qkv32, L.attention_norm.weight, L.attention_norm.bias)
-            w_fc1_f, b_fc1_f, cs_fc1 = fold(L.ffn.fc1.weight, L.ffn.fc1.bias, L.ffn_norm.weight, L.ffn_norm.bias)
+            folded = {}
+            if self.fuse_layernorm:
+                w_qkv32 = torch.cat([a.query.weight, a.key.weight, a.value.weight], 0)
+                b_qkv32 = torch.cat([a.query.bias, a.key.bias, a.value.bias], 0)
+                w_qkv_f, b_qkv_f, cs_qkv = fold(w_qkv32, b_qkv32, L.attention_norm.weight, L.attention_norm.bias)
+                w_fc1_f, b_fc1_f, cs_fc1 = fold(L.ffn.fc1.weight, L.ffn.fc1.bias, L.ffn_norm.weight, L.ffn_norm.bias)
+                folded = dict(w_qkv_f=w_qkv_f, b_qkv_f=b_qkv_f, cs_qkv=cs_qkv, w_fc1_f=w_fc1_f, b_fc1_f=b_fc1_f,
+                              cs_fc1=cs_fc1)
             self.layers.append(_LayerPack(
-                w_qkv_f=w_qkv_f, b_qkv_f=b_qkv_f, cs_qkv=cs_qkv, w_fc1_f=w_fc1_f, b_fc1_f=b_fc1_f, cs_fc1=cs_fc1,
+                **folded,
                 ln1_w=f32(L.attention_norm.weight), ln1_b=f32(L.attention_norm.bias),
                 w_qkv=h16(torch.cat([a.query.weight, a.key.weight, a.value.weight], 0)),
                 b_qkv=f32(torch.cat([a.query.bias, a.key.bias, a.value.bias], 0)),
@@ -247,7 +258,7 @@ class Engine:
         lin1, pre, lin2 = m.q_predictor[1], m.q_predictor[2], m.q_predictor[4]
         self.head_hidden = lin1.weight.shape[0]
         plist += [f32(lin1.weight), f32(lin1.bias), f32(pre.weight), f32(lin2.weight), f32(lin2.bias)]
-        self._tail_tensors = plist  # keep alive
+        self._tail_tensors = plist  # keep alive (detached views of the live parameters)
         arr = (C.c_void_p * len(plist))(*[None if t is None else t.data_ptr() for t in plist])
         self._tail_params = arr
         self.token_num = int(getattr(m, "token_num", 0))
@@ -255,15 +266,26 @@ class Engine:
     # ------------------------------------------------------------------ workspaces
     def workspace(self, B: int, N: int, streams: int = 2) -> _Workspace:
         self._ensure_ready()
-        ws = self._ws.get((B, N, streams))
+        key = (B, N, streams)
+        ws = self._ws.get(key)
         if ws is None:
-            ws = self._ws[(B, N, streams)] = _Workspace(self, B, N, streams)
+            while len(self._ws) >= max(self.max_workspaces, 1):   # least-recently-used (B, N) goes first
+                self._ws.popitem(last=False)
+            with torch.cuda.device(self.device):
+                ws = self._ws[key] = _Workspace(self, B, N, streams)
+        else:
+            self._ws.move_to_end(key)
         return ws
 
+    def clear_workspaces(self):
+        """Drop every cached activation workspace and captured graph (they are re-created on demand)."""
+        self._ws.clear()
+
     # ------------------------------------------------------------------ launch sequence
-    def _encode_and_score(self, ws: _Workspace, embedded: bool):
-        """Everything after the inputs sit in ws.patches16 / ws.proj, ws.pos, ws.scales."""
-        c, st, dt = self._call, _stream(), self.vtq16
+    def _encode_and_score(self, ws: _Workspace, embedded: bool, tail: bool = True):
+        """Everything after the inputs sit in ws.patches16 / ws.proj, ws.pos, ws.scales.  ``tail=False`` stops after
+        the encoder with ws.diff = LN(cls_ref) - LN(cls_dist) (no diff_scale): the differentiable tail takes over."""
+        c, st, dt = self._call, _stream(self.device), self.vtq16
         B, N, S, H = ws.B, ws.N, ws.S, self.hidden
         n_seq, rows, prow = ws.streams * B, ws.streams * B * S, ws.streams * B * N
         if not embedded:
@@ -333,36 +355,43 @@ class Engine:
               EPI_BIAS_RESID_F32, _ptr(ws.x), 0, _ptr(L.g2), st)
         for k in range(1, ws.streams):   # every distorted block against the (once-encoded) reference block
             c("cls_diff", "vtq_cls_diff", _ptr(ws.x), C.c_void_p(ws.x.data_ptr() + k * B * S * H * 4), B, S, H,
-              self.token_num, _ptr(self.lnf_w), _ptr(self.lnf_b), eps, _ptr(self.diff_gamma),
+              self.token_num, _ptr(self.lnf_w), _ptr(self.lnf_b), eps, _ptr(self.diff_gamma) if tail else None,
               C.c_void_p(ws.diff.data_ptr() + (k - 1) * B * H * 4), st)
+        if not tail:
+            return
         nq = (ws.streams - 1) * B
         c("diffnet_head", "vtq_diffnet_head", _ptr(ws.diff), self._tail_params, len(self._tail_params), self.num_rgs,
           self.num_rcabs, H, self.ca_hidden, self.head_hidden, nq, _ptr(ws.q), _ptr(ws.tail_ws), st)
 
-    def run(self, ws: _Workspace, embedded: bool = False):
+    def run(self, ws: _Workspace, embedded: bool = False, tail: bool = True):
         """Encode + score the staged inputs; uses a captured CUDA graph per workspace when enabled."""
-        if not self.use_cuda_graph or self.dump_indices or self.timeline is not None:
-            self._encode_and_score(ws, embedded)
-            return
-        key = ("emb" if embedded else "patch", self.prune_last_block, self.fuse_layernorm)
-        if ws.graph is None or ws.graph[0] != key:
-            # warm-up outside capture (cudaFuncSetAttribute, lazy module load), then capture
-            self._encode_and_score(ws, embedded)
-            torch.cuda.current_stream().synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                self._encode_and_score(ws, embedded)
-            ws.graph = (key, g)
-        ws.graph[1].replay()
+        with torch.cuda.device(self.device):
+            if not self.use_cuda_graph or self.dump_indices or self.timeline is not None:
+                self._encode_and_score(ws, embedded, tail)
+                return
+            key = ("emb" if embedded else "patch", self.prune_last_block, self.fuse_layernorm, tail)
+            if ws.graph is None or ws.graph[0] != key:
+                # warm-up outside capture (cudaFuncSetAttribute, lazy module load), then capture
+                self._encode_and_score(ws, embedded, tail)
+                torch.cuda.current_stream(self.device).synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    self._encode_and_score(ws, embedded, tail)
+                ws.graph = (key, g)
+            ws.graph[1].replay()
 
     # ------------------------------------------------------------------ input staging
     def stage_patches(self, ws: _Workspace, patches, pos, scales):
         """Reference-style inputs: tuples (ref, dist) of (B,N,3,P,P) fp32 [or (B,N,H) embedded], (B,N,2), (B,N)."""
-        c, st = self.ctx.call, _stream()
+        c, st = self.ctx.call, _stream(self.device)
         B, N = ws.B, ws.N
         embedded = patches[0].dim() == 3
+        dev = self.device
+        # the reference runs on whatever device its inputs live on; here raw pointers go to the kernels, so inputs are
+        # brought to the model's device first (a CPU tensor's data_ptr must never reach a launch)
+        on_dev = lambda t: t if t.device == dev else t.to(dev, non_blocking=True)
         for img in range(ws.streams):
-            p = patches[img]
+            p = on_dev(patches[img])
             if p.dtype != torch.float32 or not p.is_contiguous():
                 p = p.to(torch.float32).contiguous()
             if embedded:
@@ -370,9 +399,9 @@ class Engine:
             else:
                 c("vtq_cast_rows", _ptr(p), C.c_void_p(ws.patches16[img * B * N].data_ptr()), p.numel(), self.vtq16, st)
             if self.pos_table is not None:
-                ws.pos[img * B * N:(img + 1) * B * N].copy_(pos[img].reshape(B * N, 2))
+                ws.pos[img * B * N:(img + 1) * B * N].copy_(on_dev(pos[img]).reshape(B * N, 2))
             if self.scale_table is not None:
                 if scales is None or scales[img] is None:
                     raise ValueError("Model uses scale embedding but scales is passed as None.")
-                ws.scales[img * B * N:(img + 1) * B * N].copy_(scales[img].reshape(B * N))
+                ws.scales[img * B * N:(img + 1) * B * N].copy_(on_dev(scales[img]).reshape(B * N))
         return embedded

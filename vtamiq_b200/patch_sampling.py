@@ -93,14 +93,16 @@ def sample_batch(batch: int, h: int, w: int, patch_count: int, patch_dim: int = 
     return out
 
 
-def _pyramid(ctx, level0: torch.Tensor, num_levels: int):
-    """[planes..., H, W] fp32 -> list of levels; level s+1 = 2x2 mean of level s (floor mode)."""
-    levels = [level0]
-    for _ in range(1, num_levels):
+def _pyramid(ctx, level0: torch.Tensor, num_levels: int, levels=None):
+    """[planes..., H, W] fp32 -> list of levels; level s+1 = 2x2 mean of level s (floor mode).  ``levels`` may hold
+    already-built leading levels (level 0 may be None when it was never materialised)."""
+    levels = [level0] if levels is None else list(levels)
+    dev = levels[-1].device
+    while len(levels) < num_levels:
         src = levels[-1]
         H, W = src.shape[-2:]
-        dst = torch.empty(*src.shape[:-2], H // 2, W // 2, dtype=torch.float32, device=src.device)
-        ctx.call("vtq_avgpool2x2", _ptr(src), _ptr(dst), src.numel() // (H * W), H, W, _stream())
+        dst = torch.empty(*src.shape[:-2], H // 2, W // 2, dtype=torch.float32, device=dev)
+        ctx.call("vtq_avgpool2x2", _ptr(src), _ptr(dst), src.numel() // (H * W), H, W, _stream(dev))
         levels.append(dst)
     return levels
 
@@ -109,48 +111,92 @@ def _normalize_u8(ctx, images_u8: torch.Tensor) -> torch.Tensor:
     """uint8 (..., H, W, 3) -> normalised fp32 (..., 3, H, W) with the reference's transform arithmetic."""
     lead, (H, W) = images_u8.shape[:-3], images_u8.shape[-3:-1]
     out = torch.empty(*lead, 3, H, W, dtype=torch.float32, device=images_u8.device)
-    ctx.call("vtq_normalize_u8", _ptr(images_u8), _ptr(out), images_u8.numel() // (3 * H * W), H, W, _stream())
+    ctx.call("vtq_normalize_u8", _ptr(images_u8), _ptr(out), images_u8.numel() // (3 * H * W), H, W,
+             _stream(images_u8.device))
     return out
 
 
-def gather_into_workspace(eng, ws, images: torch.Tensor, samples):
+def _u8_levels(ctx, images_u8: torch.Tensor, num_levels: int):
+    """Pyramid of decoded uint8 (..., H, W, 3) images WITHOUT an fp32 level 0: level 0 stays uint8 (gathered with the
+    transform fused), level 1 = transform + 2x2 mean in one pass, coarser levels from level 1.
+    Returns [None | fp32 level0, level1, ...] (level 0 is only materialised when W % 8 != 0)."""
+    lead, (H, W) = images_u8.shape[:-3], images_u8.shape[-3:-1]
+    if num_levels == 1:
+        return [None]
+    if W % 8 != 0:
+        f32 = _normalize_u8(ctx, images_u8)
+        return _pyramid(ctx, f32, num_levels)
+    l1 = torch.empty(*lead, 3, H // 2, W // 2, dtype=torch.float32, device=images_u8.device)
+    ctx.call("vtq_avgpool2x2_u8", _ptr(images_u8), _ptr(l1), images_u8.numel() // (3 * H * W), H, W,
+             _stream(images_u8.device))
+    return _pyramid(ctx, None, num_levels, levels=[None, l1])
+
+
+def check_coordinates(ctx, sync: bool):
+    """Raise IndexError (as torch's advanced indexing does in the reference gather, patch_sampling.py:531-545) when a
+    gather launch saw a patch origin outside [0, H-16] x [0, W-16].  The kernels clamp such origins (no out-of-bounds
+    read) and raise a flag in pinned host memory; ``sync`` waits for the launches queued so far, otherwise the flag
+    reflects the launches that have already finished (checked again at the next call)."""
+    if sync:
+        torch.cuda.current_stream(torch.device("cuda", ctx.device)).synchronize()
+    if ctx.coord_status(reset=True):
+        raise IndexError("vtamiq_b200 patch gather: a sampled patch origin lies outside the image "
+                         "(valid range [0, H-16] x [0, W-16]); the reference's gather raises IndexError here")
+
+
+def _check_samples(smp, B, n=None):
+    if smp.dtype != torch.float64 or smp.dim() != 3 or smp.shape[0] != B or smp.shape[1] != 2 or \
+            (n is not None and smp.shape[2] != n):
+        raise ValueError("samples[s] must be float64 (B, 2, n_s)")
+
+
+def gather_into_workspace(eng, ws, images: torch.Tensor, samples, validate: str = "lazy"):
     """Fill ws.patches16 / ws.pos / ws.scales for ``Engine.run`` from images + per-scale coordinates.
-    images: (2,B,3,H,W) fp32 normalised, or (2,B,H,W,3) uint8 as decoded (transform fused into the gather)."""
-    if images.dtype == torch.uint8:
+    images: (2,B,3,H,W) fp32 normalised, or (2,B,H,W,3) uint8 as decoded (transform fused into the gather).
+    validate: "lazy" (default: out-of-range coordinates of EARLIER, finished launches raise IndexError now; this
+    call's are reported by the next call or by ``check_coordinates``), "sync" (wait and raise for this call),
+    "off"."""
+    dev = eng.device
+    if images.device != dev:
+        raise ValueError(f"images must live on the model's device ({dev}), got {images.device}")
+    samples = [s if s.device == dev else s.to(dev) for s in samples]   # a host pointer must never reach a launch
+    if validate != "off":
+        check_coordinates(eng.ctx, sync=False)
+    st = _stream(dev)
+    use_scales = eng.scale_table is not None
+    sc_ptr = _ptr(ws.scales) if use_scales else None
+    u8 = images.dtype == torch.uint8
+    if u8:
         if images.dim() != 5 or images.shape[0] != 2 or images.shape[4] != 3:
             raise ValueError("uint8 images must be (2, B, H, W, 3)")
         images = images.contiguous()
-        B, H, W = images.shape[1], images.shape[2], images.shape[3]
-        if len(samples) == 1:
-            smp = samples[0]
-            if smp.dtype != torch.float64 or smp.shape[0] != B or smp.shape[1] != 2 or smp.shape[2] != ws.N:
-                raise ValueError("samples[0] must be float64 (B, 2, N)")
-            eng.ctx.call("vtq_patch_gather_u8", _ptr(images), 2 * B, H, W, _ptr(smp.contiguous()), B, ws.N, None,
-                         _ptr(ws.patches16), eng.vtq16, _ptr(ws.pos), _stream())
-            if eng.scale_table is not None:
-                ws.scales.zero_()
-            return
-        images = _normalize_u8(eng.ctx, images)   # multi-scale: the pyramid is built from the fp32 image
-    if images.dim() != 5 or images.shape[0] != 2 or images.shape[2] != 3:
-        raise ValueError("images must be (2, B, 3, H, W)")
-    if images.dtype != torch.float32 or not images.is_contiguous():
-        images = images.to(torch.float32).contiguous()
-    B = images.shape[1]
-    levels = _pyramid(eng.ctx, images, len(samples))
-    use_scales = eng.scale_table is not None
+        B = images.shape[1]
+        levels = _u8_levels(eng.ctx, images, len(samples))
+    else:
+        if images.dim() != 5 or images.shape[0] != 2 or images.shape[2] != 3:
+            raise ValueError("images must be (2, B, 3, H, W)")
+        if images.dtype != torch.float32 or not images.is_contiguous():
+            images = images.to(torch.float32).contiguous()
+        B = images.shape[1]
+        levels = _pyramid(eng.ctx, images, len(samples))
     off = 0
     for s, (lvl, smp) in enumerate(zip(levels, samples)):
-        if smp.dtype != torch.float64 or smp.shape[0] != B or smp.shape[1] != 2:
-            raise ValueError("samples[s] must be float64 (B, 2, n_s)")
+        _check_samples(smp, B)
         smp = smp.contiguous()
         n = smp.shape[2]
-        H, W = lvl.shape[-2:]
-        eng.ctx.call("vtq_patch_gather", _ptr(lvl), 2 * B, H, W, _ptr(smp), B, n, off, ws.N, None,
-                     _ptr(ws.patches16), eng.vtq16, _ptr(ws.pos), _ptr(ws.scales) if use_scales else None, s,
-                     _stream())
+        if lvl is None:      # level 0 straight from the decoded image
+            H, W = images.shape[2], images.shape[3]
+            eng.ctx.call("vtq_patch_gather_u8", _ptr(images), 2 * B, H, W, _ptr(smp), B, n, off, ws.N, None,
+                         _ptr(ws.patches16), eng.vtq16, _ptr(ws.pos), sc_ptr, s, st)
+        else:
+            H, W = lvl.shape[-2:]
+            eng.ctx.call("vtq_patch_gather", _ptr(lvl), 2 * B, H, W, _ptr(smp), B, n, off, ws.N, None,
+                         _ptr(ws.patches16), eng.vtq16, _ptr(ws.pos), sc_ptr, s, st)
         off += n
     if off != ws.N:
         raise ValueError("sample counts do not add up to the workspace's patch count")
+    if validate == "sync":
+        check_coordinates(eng.ctx, sync=True)
 
 
 def extract_patches(tensors: torch.Tensor, samples, patch_dim: int = 16, with_scales: bool | None = None):
@@ -166,20 +212,10 @@ def extract_patches(tensors: torch.Tensor, samples, patch_dim: int = 16, with_sc
     if tensors.device.type != "cuda":
         raise RuntimeError("extract_patches runs on the GPU only (no CPU path)")
     ctx = get_context(tensors.device.index if tensors.device.index is not None else torch.cuda.current_device())
-    if tensors.dtype == torch.uint8:      # (K, H, W, 3) as decoded: fuse / apply the reference transform on device
+    u8 = tensors.dtype == torch.uint8     # (K, H, W, 3) as decoded: the reference transform is applied on device
+    if u8:
         tensors = tensors.contiguous()
-        if len(samples) == 1:
-            K, H, W = tensors.shape[0], tensors.shape[1], tensors.shape[2]
-            sm = torch.as_tensor(np.asarray(samples[0]), dtype=torch.float64).to(tensors.device).reshape(1, 2, -1).contiguous()
-            N = sm.shape[-1]
-            patches = torch.zeros(K, N, 3, patch_dim, patch_dim, dtype=torch.float32, device=tensors.device)
-            pos = torch.zeros(K, N, 2, dtype=torch.float32, device=tensors.device)
-            ctx.call("vtq_patch_gather_u8", _ptr(tensors), K, H, W, _ptr(sm), 1, N, _ptr(patches), None, VTQ_F16,
-                     _ptr(pos), _stream())
-            sc = torch.zeros(K, N, dtype=torch.int32, device=tensors.device) if with_scales else None
-            return patches, pos, sc
-        tensors = _normalize_u8(ctx, tensors)
-    if tensors.dtype != torch.float32 or not tensors.is_contiguous():
+    elif tensors.dtype != torch.float32 or not tensors.is_contiguous():
         tensors = tensors.to(torch.float32).contiguous()
     K = tensors.shape[0]
     dev = tensors.device
@@ -189,14 +225,21 @@ def extract_patches(tensors: torch.Tensor, samples, patch_dim: int = 16, with_sc
     patches = torch.zeros(K, N, 3, patch_dim, patch_dim, dtype=torch.float32, device=dev)
     pos = torch.zeros(K, N, 2, dtype=torch.float32, device=dev)
     scales = torch.zeros(K, N, dtype=torch.float32, device=dev) if use_scales else None
-    levels = _pyramid(ctx, tensors, len(smp))
+    levels = _u8_levels(ctx, tensors, len(smp)) if u8 else _pyramid(ctx, tensors, len(smp))
+    check_coordinates(ctx, sync=False)
     off = 0
     for s, (lvl, sm) in enumerate(zip(levels, smp)):
-        H, W = lvl.shape[-2:]
         n = sm.shape[-1]
-        ctx.call("vtq_patch_gather", _ptr(lvl), K, H, W, _ptr(sm), 1, n, off, N, _ptr(patches), None, VTQ_F16,
-                 _ptr(pos), _ptr(scales), s, _stream())
+        if lvl is None:
+            H, W = tensors.shape[1], tensors.shape[2]
+            ctx.call("vtq_patch_gather_u8", _ptr(tensors), K, H, W, _ptr(sm), 1, n, off, N, _ptr(patches), None,
+                     VTQ_F16, _ptr(pos), _ptr(scales), s, _stream(dev))
+        else:
+            H, W = lvl.shape[-2:]
+            ctx.call("vtq_patch_gather", _ptr(lvl), K, H, W, _ptr(sm), 1, n, off, N, _ptr(patches), None, VTQ_F16,
+                     _ptr(pos), _ptr(scales), s, _stream(dev))
         off += n
+    check_coordinates(ctx, sync=True)   # reference-format API: raise for THIS call, like the reference does
     return patches, pos, (scales.to(torch.int32) if use_scales else None)
 
 

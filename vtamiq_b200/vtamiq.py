@@ -4,7 +4,8 @@ Boundary being honoured: constructor kwargs of ``modules/vtamiq
 ``modules/VisionTransformer/backbone.py:17-33``; ``forward(patches, pos, scales) -> (q, None)``
 (vtamiq.py:94-119); ``set_freeze_state`` (vtamiq.py:81-92, backbone.py:62-106); identical
 ``state_dict`` keys / shapes; ``transformer.load_from(npz)``.  The forward itself is the sm_100a kernel
-sequence in :mod:`vtamiq_b200.engine` — inference only, no CPU / eager fallback.
+sequence in :mod:`vtamiq_b200.engine` — no CPU / eager fallback.  Inference everywhere; training (autograd) for the
+parameters behind the encoder, i.e. the reference's frozen-encoder fine-tuning (:mod:`vtamiq_b200.tail_autograd`).
 """
 from __future__ import annotations
 
@@ -91,6 +92,7 @@ class VTAMIQ(VisionTransformerBackbone):
         self.quality_decoder = make_quality_decoder(hidden, num_rgs, num_rcabs, ca_reduction) if calibrate \
             else nn.Sequential()
         self.predictor_dropout = predictor_dropout
+        self.rg_path_drop = rg_path_drop   # DropPath of every ResidualGroup branch (training mode only)
         self.q_predictor = nn.Sequential(
             nn.Dropout(predictor_dropout),
             nn.Linear(hidden, hidden // 4),
@@ -114,16 +116,34 @@ class VTAMIQ(VisionTransformerBackbone):
         if freeze_dict["freeze_q_predictor"]:
             set_grad(self.q_predictor, rg)
 
-    def _check_inference(self):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise RuntimeError(
-                "vtamiq_b200.VTAMIQ implements the inference path only (model.eval() + torch.no_grad()); "
-                "training/backward is not provided by the sm_100a kernels")
+    # -- what the kernels cover ------------------------------------------------------------------
+    def _grad_mode(self, inputs=()):
+        """"none": plain inference.  "tail": autograd is recording and only parameters BEHIND the encoder
+        (diff_scale, quality_decoder, q_predictor) want gradients — the reference's frozen-encoder fine-tuning
+        (set_freeze_state, backbone.py:62-106; train.py:799,:833): the encoder runs forward-only on the inference
+        kernels and the tail runs through the differentiable kernels (vtamiq_b200/tail_autograd.py).
+        Anything that would need a backward pass through the encoder raises instead of silently returning a
+        detached score."""
+        if not torch.is_grad_enabled():
+            return "none"
+        if any(torch.is_tensor(t) and t.requires_grad for grp in inputs if grp is not None for t in grp):
+            raise NotImplementedError(
+                "vtamiq_b200.VTAMIQ: gradients with respect to the inputs need a backward pass through the encoder, "
+                "which the sm_100a kernels do not provide; call under torch.no_grad()")
+        enc = [n for n, p in self.transformer.named_parameters() if p.requires_grad]
+        tail = any(p.requires_grad for m in (self.diff_scale, self.quality_decoder, self.q_predictor)
+                   for p in m.parameters())
+        if enc:
+            raise NotImplementedError(
+                "vtamiq_b200.VTAMIQ: encoder parameters require grad (e.g. " + enc[0] + ") but only the tail "
+                "(diff_scale / quality_decoder / q_predictor) has a backward pass; freeze the encoder with "
+                "set_freeze_state(True, ...) / requires_grad_(False), or run under torch.no_grad()")
+        return "tail" if tail else "none"
 
     def forward(self, patches, pos, scales):
         """patches/pos/scales: 2-tuples (ref, dist) exactly as train.py:308 passes them → ``(q[B], None)``."""
-        self._check_inference()
         eng = self._engine
+        mode = self._grad_mode((patches, pos, scales))
         p_ref = patches[0]
         B, N = p_ref.shape[0], p_ref.shape[1]
         if patches[1].shape != p_ref.shape:
@@ -134,9 +154,18 @@ class VTAMIQ(VisionTransformerBackbone):
             raise ValueError("vtamiq_b200.VTAMIQ needs at least one patch per image")
         with torch.no_grad():
             ws = eng.workspace(B, N)
-            embedded = eng.stage_patches(ws, patches, pos, scales)
-            eng.run(ws, embedded)
-            return ws.q.clone(), None
+            with torch.cuda.device(eng.device):
+                embedded = eng.stage_patches(ws, patches, pos, scales)
+                if mode == "none" and not self.training:
+                    eng.run(ws, embedded)
+                    return ws.q.clone(), None
+                eng.run(ws, embedded, tail=False)
+        return self._differentiable_tail(ws, 1)[0], None
+
+    def _differentiable_tail(self, ws, n_dist):
+        """DiffNet + head through the autograd-aware kernels (training-mode DropPath / Dropout included)."""
+        from .tail_autograd import run_tail
+        return run_tail(self, ws, n_dist)
 
     def forward_pairwise(self, patches, pos, scales):
         """Pairwise mode of ``train.predict`` (train.py:281-301): the reference calls the model twice, once per
@@ -144,44 +173,81 @@ class VTAMIQ(VisionTransformerBackbone):
         the encoder once (3B sequences instead of 4B) and both distorted blocks are scored against the shared
         reference.  patches/pos/scales: 3-tuples (ref, dist1, dist2).  Returns (q1, q2), identical to
         ``forward((ref, dist1), ...)[0]`` and ``forward((ref, dist2), ...)[0]``."""
-        self._check_inference()
         eng = self._engine
         if len(patches) != 3:
             raise ValueError("forward_pairwise expects (ref, dist1, dist2) tuples")
+        mode = self._grad_mode((patches, pos, scales))
         B, N = patches[0].shape[0], patches[0].shape[1]
         with torch.no_grad():
             ws = eng.workspace(B, N, streams=3)
-            embedded = eng.stage_patches(ws, patches, pos, scales if scales is not None else (None,) * 3)
-            eng.run(ws, embedded)
-            q = ws.q.clone()
-            return q[:B], q[B:]
+            with torch.cuda.device(eng.device):
+                embedded = eng.stage_patches(ws, patches, pos, scales if scales is not None else (None,) * 3)
+                if mode == "none" and not self.training:
+                    eng.run(ws, embedded)
+                    q = ws.q.clone()
+                    return q[:B], q[B:]
+                eng.run(ws, embedded, tail=False)
+        return self._differentiable_tail(ws, 2)
 
     # -- fast entry: gather on device ------------------------------------------------------------
-    def forward_from_images(self, images, samples, return_inputs=False):
+    def forward_from_images(self, images, samples, return_inputs=False, validate="lazy"):
         """Device-side patch extraction fused in front of the forward.
 
         images  : (2, B, 3, H, W) fp32 on the model's device, already normalised ((x-.5)/.5), [0] = ref block;
                   or (2, B, H, W, 3) uint8 as decoded — the reference's to_tensor + normalize arithmetic is then
-                  applied on the device (fused into the gather when a single scale is sampled), bit-identically.
+                  applied on the device inside the gather (and inside the first pyramid level), bit-identically.
         samples : list over scales s=0.. of float64 (B, 2, n_s) top-left coordinates in the level-s image
                   (row 0 = y), as ``PatchSampler.get_sample_params`` returns them; ref and dist share them.
+        validate: coordinate-range check, see ``patch_sampling.gather_into_workspace`` ("lazy" | "sync" | "off").
         Returns q (B,), or (q, (patches16, pos, scales)) views of the staged inputs when return_inputs.
         """
         from .patch_sampling import gather_into_workspace
-        self._check_inference()
         eng = self._engine
+        mode = self._grad_mode()
+        B = images.shape[1]
+        N = int(sum(s.shape[-1] for s in samples))
         with torch.no_grad():
-            B = images.shape[1]
-            N = int(sum(s.shape[-1] for s in samples))
-            if images.device != next(self.parameters()).device:
-                raise ValueError("images must live on the model's device")
             ws = eng.workspace(B, N)
-            gather_into_workspace(eng, ws, images, samples)
-            eng.run(ws, embedded=False)
-            q = ws.q.clone()
+            with torch.cuda.device(eng.device):
+                gather_into_workspace(eng, ws, images, samples, validate=validate)
+                if mode == "none" and not self.training:
+                    eng.run(ws, embedded=False)
+                    q = ws.q.clone()
+                else:
+                    eng.run(ws, embedded=False, tail=False)
+        if not (mode == "none" and not self.training):
+            q = self._differentiable_tail(ws, 1)[0]
         if return_inputs:
             return q, (ws.patches16, ws.pos, ws.scales)
         return q
+
+    # -- the engine holds ctypes handles / device workspaces: never copied or pickled with the module -----------
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k != "_engine":
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        old = self._engine
+        object.__setattr__(new, "_engine", Engine(new, operand_dtype=old.operand_dtype,
+                                                  use_cuda_graph=old.use_cuda_graph,
+                                                  prune_last_block=old.prune_last_block,
+                                                  fuse_layernorm=old.fuse_layernorm))
+        return new
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        old = state.pop("_engine")
+        state["_engine_args"] = dict(operand_dtype=old.operand_dtype, use_cuda_graph=old.use_cuda_graph,
+                                     prune_last_block=old.prune_last_block, fuse_layernorm=old.fuse_layernorm)
+        return state
+
+    def __setstate__(self, state):
+        args = state.pop("_engine_args", {})
+        self.__dict__.update(state)
+        object.__setattr__(self, "_engine", Engine(self, **args))
 
     @property
     def engine(self) -> Engine:
