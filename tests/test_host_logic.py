@@ -351,12 +351,12 @@ def test_bench_reference_arm_contract():
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, OMP_NUM_THREADS=str(min(8, os.cpu_count() or 1)))
+    env = dict(os.environ, OMP_NUM_THREADS=str(min(8, os.cpu_count() or 1)), VTQ_CPU_BUDGET_S="4")
     other = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
                            cwd=root, env=dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"), capture_output=True, text=True,
                            timeout=300)
     assert other.returncode == 0 and other.stdout.strip() == ""
-    run = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "1"], cwd=root,
+    run = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "2", "--warmup", "1"], cwd=root,
                          env=env, capture_output=True, text=True, timeout=600)
     assert run.returncode == 0, run.stderr[-2000:]
     lines = [ln for ln in run.stdout.splitlines() if ln.strip()]
@@ -365,8 +365,37 @@ def test_bench_reference_arm_contract():
     assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["higher_is_better"] is True and d["value"] > 0
     for key in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config"):
         assert key in d, key
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    from oracle import reference_runner
+    want_kind = "reference" if reference_runner.available() else "port"
+    assert d["cpu_baseline"]["kind"] == want_kind and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # the steps it reports are the steps it ran: value = pairs per step * steps / (steps * ms_per_step)
+    assert d["steps"] == 2 and d["warmup"] == 1
+    assert abs(d["value"] - d["pairs_per_cpu_step"] / (d["ms_per_step"] / 1e3)) <= 1e-6 * d["value"]
+    # same workload description as the GPU arm prints for the same command line (the driver matches the two lines)
+    import bench
+    import argparse
+    wl = bench.Workload(argparse.Namespace(config="cfg2", pairs=0, global_pairs=0, images="uint8"), 1, 0)
+    assert d["config"] == wl.config and d["config"]["name"] == "cfg2" and d["config"]["pairs_per_step"] == 32
+
+
+def test_bench_workloads_follow_baseline_configs():
+    """bench.py --config: shapes of BASELINE.json's five configurations, weak and strong sharding."""
+    import argparse
+    import bench
+    ns = lambda **k: argparse.Namespace(**{**dict(config="cfg2", pairs=0, global_pairs=0, images="uint8"), **k})
+    shapes = {name: (bench.Workload(ns(config=name), 1, 0)) for name in bench.CONFIGS}
+    assert (shapes["cfg1"].B, shapes["cfg1"].N, shapes["cfg1"].H, shapes["cfg1"].W) == (1, 256, 384, 512)
+    assert (shapes["cfg2"].B, shapes["cfg2"].N) == (32, 500)
+    assert (shapes["cfg3"].B, shapes["cfg3"].counts, shapes["cfg3"].H, shapes["cfg3"].vit) == (64, (380, 96, 24), 1024, {"num_scales": 3})
+    assert (shapes["cfg4"].B, shapes["cfg4"].N, shapes["cfg4"].H, shapes["cfg4"].W, shapes["cfg4"].S) == (8, 5000, 2160, 3840, 5001)
+    assert 256 <= shapes["cfg5"].B <= 2048
+    weak = bench.Workload(ns(config="cfg5", pairs=256), 8, 3)
+    assert (weak.B, weak.total_pairs, weak.scaling) == (256, 2048, "weak")
+    strong = [bench.Workload(ns(config="cfg5", global_pairs=2050), 8, r) for r in range(8)]
+    assert sum(w.B for w in strong) == 2050 and {w.B for w in strong} == {256, 257} and strong[0].scaling == "strong"
+    fp = bench.flops_per_pair(500)
+    assert abs(fp["total"] / 1e9 - 189.92) < 0.01 and abs(bench.flops_per_pair(5000)["total"] / 1e9 - 3554.8) < 0.1
 
 
 def test_u8_transform_is_exact():

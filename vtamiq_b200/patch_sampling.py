@@ -93,6 +93,10 @@ def sample_batch(batch: int, h: int, w: int, patch_count: int, patch_dim: int = 
     return out
 
 
+def _as_call(ctx_or_call):
+    return ctx_or_call.call if hasattr(ctx_or_call, "call") else ctx_or_call
+
+
 def _pyramid(ctx, level0: torch.Tensor, num_levels: int, levels=None):
     """[planes..., H, W] fp32 -> list of levels; level s+1 = 2x2 mean of level s (floor mode).  ``levels`` may hold
     already-built leading levels (level 0 may be None when it was never materialised)."""
@@ -102,7 +106,7 @@ def _pyramid(ctx, level0: torch.Tensor, num_levels: int, levels=None):
         src = levels[-1]
         H, W = src.shape[-2:]
         dst = torch.empty(*src.shape[:-2], H // 2, W // 2, dtype=torch.float32, device=dev)
-        ctx.call("vtq_avgpool2x2", _ptr(src), _ptr(dst), src.numel() // (H * W), H, W, _stream(dev))
+        _as_call(ctx)("vtq_avgpool2x2", _ptr(src), _ptr(dst), src.numel() // (H * W), H, W, _stream(dev))
         levels.append(dst)
     return levels
 
@@ -111,8 +115,8 @@ def _normalize_u8(ctx, images_u8: torch.Tensor) -> torch.Tensor:
     """uint8 (..., H, W, 3) -> normalised fp32 (..., 3, H, W) with the reference's transform arithmetic."""
     lead, (H, W) = images_u8.shape[:-3], images_u8.shape[-3:-1]
     out = torch.empty(*lead, 3, H, W, dtype=torch.float32, device=images_u8.device)
-    ctx.call("vtq_normalize_u8", _ptr(images_u8), _ptr(out), images_u8.numel() // (3 * H * W), H, W,
-             _stream(images_u8.device))
+    _as_call(ctx)("vtq_normalize_u8", _ptr(images_u8), _ptr(out), images_u8.numel() // (3 * H * W), H, W,
+                  _stream(images_u8.device))
     return out
 
 
@@ -127,8 +131,8 @@ def _u8_levels(ctx, images_u8: torch.Tensor, num_levels: int):
         f32 = _normalize_u8(ctx, images_u8)
         return _pyramid(ctx, f32, num_levels)
     l1 = torch.empty(*lead, 3, H // 2, W // 2, dtype=torch.float32, device=images_u8.device)
-    ctx.call("vtq_avgpool2x2_u8", _ptr(images_u8), _ptr(l1), images_u8.numel() // (3 * H * W), H, W,
-             _stream(images_u8.device))
+    _as_call(ctx)("vtq_avgpool2x2_u8", _ptr(images_u8), _ptr(l1), images_u8.numel() // (3 * H * W), H, W,
+                  _stream(images_u8.device))
     return _pyramid(ctx, None, num_levels, levels=[None, l1])
 
 
@@ -165,20 +169,22 @@ def gather_into_workspace(eng, ws, images: torch.Tensor, samples, validate: str 
     st = _stream(dev)
     use_scales = eng.scale_table is not None
     sc_ptr = _ptr(ws.scales) if use_scales else None
+    pyr = lambda name, *a: eng._call("pyramid", name, *a)       # tagged launches (bench.py's per-kernel table)
+    gat = lambda name, *a: eng._call("patch_gather", name, *a)
     u8 = images.dtype == torch.uint8
     if u8:
         if images.dim() != 5 or images.shape[0] != 2 or images.shape[4] != 3:
             raise ValueError("uint8 images must be (2, B, H, W, 3)")
         images = images.contiguous()
         B = images.shape[1]
-        levels = _u8_levels(eng.ctx, images, len(samples))
+        levels = _u8_levels(pyr, images, len(samples))
     else:
         if images.dim() != 5 or images.shape[0] != 2 or images.shape[2] != 3:
             raise ValueError("images must be (2, B, 3, H, W)")
         if images.dtype != torch.float32 or not images.is_contiguous():
             images = images.to(torch.float32).contiguous()
         B = images.shape[1]
-        levels = _pyramid(eng.ctx, images, len(samples))
+        levels = _pyramid(pyr, images, len(samples))
     off = 0
     for s, (lvl, smp) in enumerate(zip(levels, samples)):
         _check_samples(smp, B)
@@ -186,17 +192,69 @@ def gather_into_workspace(eng, ws, images: torch.Tensor, samples, validate: str 
         n = smp.shape[2]
         if lvl is None:      # level 0 straight from the decoded image
             H, W = images.shape[2], images.shape[3]
-            eng.ctx.call("vtq_patch_gather_u8", _ptr(images), 2 * B, H, W, _ptr(smp), B, n, off, ws.N, None,
-                         _ptr(ws.patches16), eng.vtq16, _ptr(ws.pos), sc_ptr, s, st)
+            gat("vtq_patch_gather_u8", _ptr(images), 2 * B, H, W, _ptr(smp), B, n, off, ws.N, None,
+                _ptr(ws.patches16), eng.vtq16, _ptr(ws.pos), sc_ptr, s, st)
         else:
             H, W = lvl.shape[-2:]
-            eng.ctx.call("vtq_patch_gather", _ptr(lvl), 2 * B, H, W, _ptr(smp), B, n, off, ws.N, None,
-                         _ptr(ws.patches16), eng.vtq16, _ptr(ws.pos), sc_ptr, s, st)
+            gat("vtq_patch_gather", _ptr(lvl), 2 * B, H, W, _ptr(smp), B, n, off, ws.N, None,
+                _ptr(ws.patches16), eng.vtq16, _ptr(ws.pos), sc_ptr, s, st)
         off += n
     if off != ws.N:
         raise ValueError("sample counts do not add up to the workspace's patch count")
     if validate == "sync":
         check_coordinates(eng.ctx, sync=True)
+
+
+def extract_patches_batch(images: torch.Tensor, samples, with_scales: bool | None = None, validate: str = "sync"):
+    """Reference-format model inputs for a whole batch of pairs in one pass (what a DataLoader over
+    ``get_iqa_patches`` would collate, train.py:252-267).
+
+    images  : (2, B, 3, H, W) fp32 normalised or (2, B, H, W, 3) uint8 as decoded, on a CUDA device
+    samples : list over scales of float64 (B, 2, n_s) top-left coordinates (ref and dist share them)
+    returns (patches (2,B,N,3,16,16) fp32, pos (2,B,N,2) fp32, scales (2,B,N) fp32 | None): index [0] is the ref
+    block, [1] the dist block — ``model((patches[0], patches[1]), (pos[0], pos[1]), (scales[0], scales[1]))``.
+    """
+    if images.device.type != "cuda":
+        raise RuntimeError("extract_patches_batch runs on the GPU only (no CPU path)")
+    dev = images.device
+    ctx = get_context(dev.index if dev.index is not None else torch.cuda.current_device())
+    u8 = images.dtype == torch.uint8
+    if u8:
+        if images.dim() != 5 or images.shape[0] != 2 or images.shape[4] != 3:
+            raise ValueError("uint8 images must be (2, B, H, W, 3)")
+        images = images.contiguous()
+    else:
+        if images.dim() != 5 or images.shape[0] != 2 or images.shape[2] != 3:
+            raise ValueError("images must be (2, B, 3, H, W)")
+        if images.dtype != torch.float32 or not images.is_contiguous():
+            images = images.to(torch.float32).contiguous()
+    B = images.shape[1]
+    samples = [s.to(dev).contiguous() for s in samples]
+    N = int(sum(s.shape[-1] for s in samples))
+    use_scales = (len(samples) > 1) if with_scales is None else with_scales
+    patches = torch.empty(2, B, N, 3, 16, 16, dtype=torch.float32, device=dev)
+    pos = torch.empty(2, B, N, 2, dtype=torch.float32, device=dev)
+    scales = torch.empty(2, B, N, dtype=torch.float32, device=dev) if use_scales else None
+    with torch.cuda.device(dev):
+        if validate != "off":
+            check_coordinates(ctx, sync=False)
+        levels = _u8_levels(ctx, images, len(samples)) if u8 else _pyramid(ctx, images, len(samples))
+        off = 0
+        for s, (lvl, smp) in enumerate(zip(levels, samples)):
+            _check_samples(smp, B)
+            n = smp.shape[2]
+            if lvl is None:
+                H, W = images.shape[2], images.shape[3]
+                ctx.call("vtq_patch_gather_u8", _ptr(images), 2 * B, H, W, _ptr(smp), B, n, off, N, _ptr(patches), None,
+                         VTQ_F16, _ptr(pos), _ptr(scales), s, _stream(dev))
+            else:
+                H, W = lvl.shape[-2:]
+                ctx.call("vtq_patch_gather", _ptr(lvl), 2 * B, H, W, _ptr(smp), B, n, off, N, _ptr(patches), None,
+                         VTQ_F16, _ptr(pos), _ptr(scales), s, _stream(dev))
+            off += n
+        if validate == "sync":
+            check_coordinates(ctx, sync=True)
+    return patches, pos, scales
 
 
 def extract_patches(tensors: torch.Tensor, samples, patch_dim: int = 16, with_scales: bool | None = None):
