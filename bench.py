@@ -354,6 +354,7 @@ def run_gpu_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local)
+    torch.set_grad_enabled(False)     # inference: the call context of train.py:592-602 (model.eval() + no_grad)
     dev = torch.device("cuda", local)
     wl = Workload(args, world, rank)
     B = wl.B

@@ -222,6 +222,52 @@ def test_attention(ctx, dt, n_seq, S, heads):
     assert err < (3e-2 if dt == "bf16" else 4e-3), err
 
 
+def test_attention_long_sequence_5001(ctx):
+    """BASELINE cfg4's sequence length as a unit test: S = 5001 (40 key tiles per query row, ragged last tile)."""
+    n_seq, S, heads = 1, 5001, 2
+    H = heads * 64
+    g = torch.Generator(device="cuda").manual_seed(5001)
+    qkv = (torch.randn(n_seq * S, 3 * H, device="cuda", generator=g) * 1.5).half()
+    out = torch.full((n_seq * S, H), float("nan"), device="cuda", dtype=torch.float16)
+    ctx.call("vtq_attention_fwd", P(qkv), P(out), n_seq, S, heads, 0, 0, ST())
+    torch.cuda.synchronize()
+    want = _attn_ref(qkv, n_seq, S, heads)
+    assert torch.isfinite(out.float()).all()
+    assert (out.float() - want).abs().max().item() < 4e-3
+
+
+@pytest.mark.parametrize("dt", ["fp16", "bf16"])
+def test_attention_rescale_is_forced_by_score_spikes(ctx, dt):
+    """The online softmax keeps its reference maximum until the true maximum has grown by more than 2^8 (lazy
+    rescale); N(0, 1.5) inputs never get there.  Here every query row meets keys whose scores climb by ~40 (raw
+    score units, i.e. ~2^7 .. 2^58 in the exp2 domain) from one key tile to the next: key tile j carries one key
+    aligned with the queries' common direction, scaled by j.  Every tile boundary then forces the O / l correction,
+    and the planted keys dominate the softmax — the value rows they select must come out."""
+    code, tdt = DT[dt]
+    n_seq, S, heads = 2, 900, 3
+    H = heads * 64
+    g = torch.Generator(device="cuda").manual_seed(77)
+    qkv = (torch.randn(n_seq, S, 3, heads, 64, device="cuda", generator=g) * 0.5)
+    u = torch.nn.functional.normalize(torch.randn(64, device="cuda", generator=g), dim=0)
+    qkv[:, :, 0] += 6.0 * u                      # every query has a strong component along u
+    for j in range((S + 127) // 128):            # one spike key per 128-key tile, stronger in later tiles
+        pos = min(j * 128 + 37, S - 1)
+        qkv[:, pos, 1] = u * (8.0 * (j + 1))     # score ~ 6 * 8 (j+1) / 8 = 6 (j+1) after the 1/8 scale ... x log2e
+    qkv = qkv.reshape(n_seq * S, 3 * H).to(tdt)
+    out = torch.full((n_seq * S, H), float("nan"), device="cuda", dtype=tdt)
+    ctx.call("vtq_attention_fwd", P(qkv), P(out), n_seq, S, heads, code, 0, ST())
+    torch.cuda.synchronize()
+    want = _attn_ref(qkv, n_seq, S, heads)
+    assert torch.isfinite(out.float()).all()
+    err = (out.float() - want).abs().max().item()
+    assert err < (3e-2 if dt == "bf16" else 4e-3), err
+    # the growth between consecutive planted scores really exceeds the lazy-rescale threshold of 8 (exp2 domain)
+    q = qkv.view(n_seq, S, 3, heads, 64)[0, 5, 0, 0].float()
+    k0 = qkv.view(n_seq, S, 3, heads, 64)[0, 37, 1, 0].float()
+    k1 = qkv.view(n_seq, S, 3, heads, 64)[0, 165, 1, 0].float()
+    assert ((q @ k1) - (q @ k0)).item() * 0.125 * 1.4427 > 8.0
+
+
 # ------------------------------------------------------------------------------------------ row-wise kernels
 @pytest.mark.parametrize("dt", ["fp16", "bf16"])
 @pytest.mark.parametrize("rows", [1, 7, 1003])
@@ -400,3 +446,111 @@ def test_patch_gather_from_uint8_bit_exact(golden_dir, case):
     assert np.array_equal(pos.cpu().numpy().view(np.uint32), g["pos"].view(np.uint32))
     if "scales" in g.files:
         assert np.array_equal(scales.cpu().numpy(), g["scales"])
+
+
+# ------------------------------------------------------------------------------------------ K1, round 2 additions
+def _oracle_from_u8(u8_pair, smp):
+    """Reference arithmetic on decoded images: transform (to_tensor + normalize) then the numpy gather oracle."""
+    tens = np.stack([synth.to_tensor_normalized(u8_pair[k]).numpy() for k in range(u8_pair.shape[0])])
+    return patch_oracle.extract_patches(tens, smp)
+
+
+@pytest.mark.parametrize("src", ["uint8", "fp32"])
+def test_batched_gather_cfg2_shape_bit_exact_incl_16bit_operand(ctx, src):
+    """The vector gather kernels (256-bit loads, register rotation, division-free uint8 transform) at the benchmark
+    shape, one coordinate set per pair: fp32 patches / uv bit-exact against the oracle, and the 16-bit GEMM operand
+    equal to the fp32 patches rounded once."""
+    from vtamiq_b200 import extract_patches_batch
+    B, H, W, N = 3, 384, 512, 500
+    rng = np.random.default_rng(17)
+    u8 = np.stack([np.stack([synth.make_pair(p, H, W, 0.1)[k] for p in range(B)]) for k in range(2)])   # (2,B,H,W,3)
+    smp = np.stack([synth.jittered_samples(rng, H, W, N) for _ in range(B)])
+    smp[0, :, 0] = [0.0, 0.0]; smp[0, :, 1] = [H - 16.0, W - 16.0]; smp[1, :, 2] = [367.99999, 0.25]     # edges
+    if src == "uint8":
+        images = torch.from_numpy(u8).cuda()
+    else:
+        images = torch.stack([torch.stack([synth.to_tensor_normalized(u8[k, p]) for p in range(B)]) for k in range(2)]).cuda()
+    patches, pos, scales = extract_patches_batch(images, [torch.from_numpy(smp).cuda()])
+    assert scales is None
+    for p in range(B):
+        want_p, want_pos, _ = _oracle_from_u8(u8[:, p], [smp[p]])
+        assert np.array_equal(patches[:, p].cpu().numpy().view(np.uint32), want_p.view(np.uint32)), p
+        assert np.array_equal(pos[:, p].cpu().numpy().view(np.uint32), want_pos.view(np.uint32)), p
+    # 16-bit operand written by the same kernels (what Engine consumes)
+    p16 = torch.empty(2 * B * N, 768, dtype=torch.float16, device="cuda")
+    pos2 = torch.empty(2 * B * N, 2, device="cuda")
+    s_dev = torch.from_numpy(smp).cuda()
+    name = "vtq_patch_gather_u8" if src == "uint8" else "vtq_patch_gather"
+    ctx.call(name, P(images), 2 * B, H, W, P(s_dev), B, N, 0, N, None, P(p16), 0, P(pos2), None, 0, ST())
+    torch.cuda.synchronize()
+    assert torch.equal(p16.view(2, B, N, 768), patches.reshape(2, B, N, 768).half())
+    assert torch.equal(pos2.view(2, B, N, 2), pos)
+
+
+def test_batched_multiscale_gather_from_uint8_fused_pyramid():
+    """cfg3 shape from decoded images: level 0 gathered straight from uint8, level 1 = transform + 2x2 mean in one
+    kernel (no fp32 level-0 image), level 2 pooled from level 1 — bit-exact against transform -> AvgPool2d chain."""
+    from vtamiq_b200 import extract_patches_batch
+    B, H, W = 2, 1024, 1024
+    counts = (380, 96, 24)
+    rng = np.random.default_rng(23)
+    u8 = rng.integers(0, 256, size=(2, B, H, W, 3), dtype=np.uint8)
+    smp = [np.stack([synth.jittered_samples(rng, H >> s, W >> s, n) for _ in range(B)]) for s, n in enumerate(counts)]
+    patches, pos, scales = extract_patches_batch(torch.from_numpy(u8).cuda(), [torch.from_numpy(s).cuda() for s in smp])
+    for p in range(B):
+        want_p, want_pos, want_s = _oracle_from_u8(u8[:, p], [s[p] for s in smp])
+        assert np.array_equal(patches[:, p].cpu().numpy().view(np.uint32), want_p.view(np.uint32)), p
+        assert np.array_equal(pos[:, p].cpu().numpy().view(np.uint32), want_pos.view(np.uint32)), p
+        assert np.array_equal(scales[:, p].cpu().numpy().astype(np.int64), want_s.astype(np.int64)), p
+
+
+def test_u8_transform_and_pool_kernels_bit_exact(ctx):
+    """vtq_normalize_u8 (vector and scalar shapes), vtq_avgpool2x2 (vector) and vtq_avgpool2x2_u8 against torch."""
+    g = torch.Generator().manual_seed(3)
+    for (n, H, W) in [(3, 40, 64), (2, 31, 33)]:
+        u8 = torch.randint(0, 256, (n, H, W, 3), generator=g, dtype=torch.uint8)
+        want = torch.stack([synth.to_tensor_normalized(u8[i].numpy()) for i in range(n)])
+        out = torch.empty(n, 3, H, W, device="cuda")
+        ctx.call("vtq_normalize_u8", P(u8.cuda()), P(out), n, H, W, ST())
+        torch.cuda.synchronize()
+        assert torch.equal(out.cpu(), want), (n, H, W)
+    x = torch.randn(6, 64, 96, generator=g)
+    out = torch.empty(6, 32, 48, device="cuda")
+    ctx.call("vtq_avgpool2x2", P(x.cuda()), P(out), 6, 64, 96, ST())
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), patch_oracle.avgpool2x2(x.numpy()).view(np.uint32))
+    u8 = torch.randint(0, 256, (3, 50, 72, 3), generator=g, dtype=torch.uint8)
+    want = torch.stack([synth.to_tensor_normalized(u8[i].numpy()) for i in range(3)]).numpy()
+    out = torch.empty(3, 3, 25, 36, device="cuda")
+    ctx.call("vtq_avgpool2x2_u8", P(u8.cuda()), P(out), 3, 50, 72, ST())
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), patch_oracle.avgpool2x2(want).view(np.uint32))
+
+
+def test_out_of_range_coordinates_raise_index_error(ctx):
+    """torch's advanced indexing raises IndexError in the reference gather (patch_sampling.py:531-545); here the
+    kernels clamp (no out-of-bounds read) and raise a flag that the host mirror turns into IndexError."""
+    from vtamiq_b200 import check_coordinates, extract_patches
+    H, W = 64, 96
+    tens = torch.randn(2, 3, H, W, device="cuda")
+    good = np.array([[0.0, 10.5, 48.0], [0.0, 20.25, 80.0]])
+    check_coordinates(ctx, sync=True)                      # clean slate
+    extract_patches(tens, [good])
+    for bad in ([[49.0], [0.0]], [[0.0], [81.0]], [[-1.0], [5.0]], [[float("nan")], [5.0]]):
+        with pytest.raises(IndexError, match="outside the image"):
+            extract_patches(tens, [np.array(bad, dtype=np.float64)])
+    extract_patches(tens, [good])                          # the flag does not stick
+
+
+def test_tensor_map_cache_is_hit_in_steady_state(ctx):
+    """TMA descriptors are encoded once per distinct (pointer, shape, box) and re-used on later launches."""
+    M, N, K = 512, 768, 768
+    A = torch.randn(M, K, device="cuda").half(); W = torch.randn(N, K, device="cuda").half()
+    b = torch.zeros(N, device="cuda"); out = torch.empty(M, N, device="cuda", dtype=torch.float16)
+    ctx.call("vtq_gemm", P(A), 0, P(W), P(b), M, N, K, 0, 0, P(out), 0, None, ST())
+    h0, m0 = ctx.tensor_map_stats()
+    for _ in range(3):
+        ctx.call("vtq_gemm", P(A), 0, P(W), P(b), M, N, K, 0, 0, P(out), 0, None, ST())
+    torch.cuda.synchronize()
+    h1, m1 = ctx.tensor_map_stats()
+    assert m1 == m0 and h1 - h0 == 9      # three descriptors per launch, all from the cache
