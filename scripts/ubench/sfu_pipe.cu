@@ -28,7 +28,7 @@ __device__ __forceinline__ void sts4(uint32_t addr, uint32_t a, uint32_t b, uint
 //       4 body of 1 with 1/4 of the exps as a cubic on the FMA pipe
 //       5 body of 1 with scalar FADD sums                6 body of 1 with scalar FFMA arguments
 template <int MODE>
-__global__ void __launch_bounds__(256, 1) body(const float* __restrict__ in, float* __restrict__ out, long long* cyc, int rep) {
+__global__ void __launch_bounds__(256, 1) body(const float* __restrict__ in, float* __restrict__ out, long long* cyc, int rep, int skew) {
   extern __shared__ __align__(1024) uint8_t smem[];
   float r[128];
 #pragma unroll
@@ -41,6 +41,10 @@ __global__ void __launch_bounds__(256, 1) body(const float* __restrict__ in, flo
   float acc0 = 0.f, acc1 = 0.f;
   uint64_t sa = 0, sb = 0;
   __syncthreads();
+  if (threadIdx.x >= 128 && skew > 0) {  // de-phase the second warp of every sub-partition: the two warps then run
+    const long long s0 = clock64();      // different parts of the unrolled body at any moment (as in the kernel)
+    while (clock64() - s0 < skew) {}
+  }
   const long long t0 = clock64();
   for (int it = 0; it < rep; ++it) {
     const uint64_t nmc2 = pk(nmc, nmc);
@@ -88,17 +92,17 @@ __global__ void __launch_bounds__(256, 1) body(const float* __restrict__ in, flo
 }
 
 template <int MODE>
-void run(const char* name, const float* in, float* out, long long* cyc) {
+void run(const char* name, const float* in, float* out, long long* cyc, int skew = 0) {
   const int rep = 200;
   cudaFuncSetAttribute(body<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 1024);
   for (int threads : {128, 256}) {
-    body<MODE><<<148, threads, 65536 + 1024>>>(in, out, cyc, rep);
-    body<MODE><<<148, threads, 65536 + 1024>>>(in, out, cyc, rep);
+    body<MODE><<<148, threads, 65536 + 1024>>>(in, out, cyc, rep, skew);
+    body<MODE><<<148, threads, 65536 + 1024>>>(in, out, cyc, rep, skew);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("%s: %s\n", name, cudaGetErrorString(e)); return; }
     long long h[148]; cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
     double s = 0; for (long long v : h) s += double(v);
-    printf("%-44s warps/SMSP=%d  cycles per 128-key body = %.0f\n", name, threads / 128, s / 148 / rep);
+    printf("%-44s warps/SMSP=%d skew=%4d  cycles per 128-key body = %.0f\n", name, threads / 128, skew, s / 148 / rep);
   }
 }
 
@@ -114,5 +118,7 @@ int main() {
   run<4>("4 as 1, 1/4 of exps as FMA cubic", in, out, cyc);
   run<5>("5 as 1, scalar FADD sums", in, out, cyc);
   run<6>("6 as 1, scalar FFMA arguments", in, out, cyc);
+  for (int skew : {150, 300, 600, 900, 1100}) run<1>("1 with the second warp de-phased", in, out, cyc, skew);
+  for (int skew : {300, 600}) run<0>("0 with the second warp de-phased", in, out, cyc, skew);
   return 0;
 }

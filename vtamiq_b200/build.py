@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvtamiq_b200.so")
 STAMP = LIB + ".stamp"
-SOURCES = ["api.cu", "gemm.cu", "attention.cu", "rowwise.cu", "gather.cu", "diffnet.cu", "tail_train.cu"]
+SOURCES = ["api.cu", "gemm.cu", "attention.cu", "attention_v3.cu", "attention_v5.cu", "rowwise.cu", "gather.cu", "diffnet.cu", "tail_train.cu"]
 HEADERS = ["common.cuh", "host.h", os.path.join("..", "..", "include", "vtamiq_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -51,5 +51,23 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(name: str, defines: list[str]) -> str:
+    """A/B build of the same ABI with extra -D switches: vtamiq_b200/variants/lib_<name>.so (used through the
+    VTQ_LIBRARY environment variable; never the default library)."""
+    out_dir = os.path.join(HERE, "variants")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, f"lib_{name}.so")
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        sys.stderr.write(proc.stdout + proc.stderr)
+        raise RuntimeError(f"nvcc failed building variant {name}")
+    return out
+
+
 if __name__ == "__main__":
+    if len(sys.argv) >= 3 and sys.argv[1] == "--variant":   # build.py --variant name DEF1 DEF2=3 ...
+        print(build_variant(sys.argv[2], sys.argv[3:]))
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose=True))

@@ -67,11 +67,15 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 #define VTQ_SPIN_LIMIT (1u << 22)
 #endif
 
+#ifndef VTQ_MBAR_WAIT_MODE
+#define VTQ_MBAR_WAIT_MODE 0   // 0: try_wait with a suspend-time hint, 1: plain try_wait, 2: try_wait + nanosleep back-off
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
   uint32_t spins = 0;
   while (true) {
+#if VTQ_MBAR_WAIT_MODE == 0
     // try_wait with a suspend-time hint: the thread sleeps in hardware until the phase flips (or the hint
     // expires) instead of burning issue slots that the co-resident working warps need
     asm volatile(
@@ -83,7 +87,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done)
         : "r"(addr), "r"(parity), "r"(1000000u)
         : "memory");
+#else
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+#endif
     if (done) break;
+#if VTQ_MBAR_WAIT_MODE == 2
+    __nanosleep(100);
+#endif
     if (++spins > VTQ_SPIN_LIMIT) __trap();
   }
 }
@@ -298,6 +316,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
 }
