@@ -66,6 +66,46 @@ def patches_case(name, H, W, N, n_scales, ratio, seed):
     print("patches", name, patches.shape, [s.shape for s in rec], None if scales is None else np.bincount(scales[0].numpy()))
 
 
+def patches_branch_case(name, H, W, N, n_scales, ratio, seed, aligned, shuffle, sampler_kw=None):
+    """The non-default branches of get_iqa_patches (patch_sampling.py:506-508 slot permutation, :530-531/:561 one
+    coordinate set per image, :46-222/:603-605 difference- / centre-bias-weighted sampling with the weight map pooled
+    per level).  Recorded: what the sampler returned for every draw, the weight map it was handed at every draw and
+    compute_diff's output, so the device path can be replayed through vtamiq_b200.get_iqa_patches with a stub
+    sampler."""
+    import data.patch_sampling as ps
+    ref, dist = synth.make_pair(seed, H, W, 0.1)
+    tens = (synth.to_tensor_normalized(ref), synth.to_tensor_normalized(dist))
+    smp = PatchSampler(**sampler_kw) if sampler_kw else sampler()
+    draws, diffs = [], []
+    orig = smp.get_sample_params
+
+    def spy(h, w, ho, wo, diff=None, num_samples=1, debug=False):
+        out = orig(h, w, ho, wo, diff=diff, num_samples=num_samples, debug=debug)
+        draws.append(np.array(out, dtype=np.float64, copy=True))
+        diffs.append(None if diff is None else np.array(diff, copy=True))
+        return out
+    smp.get_sample_params = spy
+    from PIL import Image
+    imgs = (Image.fromarray(ref), Image.fromarray(dist))
+    diff0 = smp.compute_diff(imgs)
+    patches, pos, scales = get_iqa_patches(imgs, tens, N, 16, smp, n_scales, scale_num_samples_ratio=ratio,
+                                           use_aligned_patches=aligned, randomize_patch_scale_order=shuffle,
+                                           random_seed=seed)
+    out = dict(ref_u8=ref, dist_u8=dist, N=N, n_scales_requested=n_scales, ratio=ratio, seed=seed, aligned=aligned,
+               shuffle=shuffle, patches=patches.numpy(), pos=pos.numpy(), n_draws=len(draws),
+               has_diff=diff0 is not None)
+    if scales is not None:
+        out["scales"] = scales.numpy()
+    if diff0 is not None:
+        out["diff0"] = np.asarray(diff0)
+    for i, (d, w) in enumerate(zip(draws, diffs)):
+        out[f"draw_{i}"] = d
+        if w is not None:
+            out[f"weight_{i}"] = w
+    np.savez_compressed(os.path.join(HERE, f"patches_{name}.npz"), **out)
+    print("patches", name, patches.shape, len(draws), "draws", None if scales is None else np.bincount(scales[0].numpy()))
+
+
 def forward_case(name, vit_cfg, vt_kwargs, B, H, W, N, n_scales, ratio):
     torch.manual_seed(0)
     model = VTAMIQ(vit_config=dict(pretrained=False, **vit_cfg), **vt_kwargs).eval()
@@ -232,6 +272,13 @@ if __name__ == "__main__":
     if "--correlations-only" in sys.argv:
         correlations_case()
         sys.exit(0)
+    if "--branches-only" in sys.argv:
+        patches_branch_case("unaligned", 128, 160, 48, 2, 2.0, seed=7, aligned=False, shuffle=False)
+        # randomize_patch_scale_order=True cannot be pinned: under this image's torch (2.11) the reference itself raises
+        # at patch_sampling.py:534 (index_put of float64 positions into a float32 tensor)
+        patches_branch_case("weighted", 128, 192, 40, 2, 2.0, seed=9, aligned=True, shuffle=False,
+                            sampler_kw=dict(centerbias_weight=0.0, diff_weight=0.6, uniform_weight=0.1, grid_type=1))  # GRID_TYPE_PERTURBED
+        sys.exit(0)
     if "--sampler-only" in sys.argv:
         sampler_draws_case()
         sys.exit(0)
@@ -243,6 +290,9 @@ if __name__ == "__main__":
     forward_case("scales3", dict(num_scales=3), {}, B=2, H=256, W=256, N=100, n_scales=3, ratio=2.0)
     forward_case("traincfg", dict(num_keep_layers=6, num_extra_tokens=8, use_layer_scale=True),
                  dict(ca_reduction=16), B=2, H=96, W=128, N=64, n_scales=1, ratio=2.0)
+    patches_branch_case("unaligned", 128, 160, 48, 2, 2.0, seed=7, aligned=False, shuffle=False)
+    patches_branch_case("weighted", 128, 192, 40, 2, 2.0, seed=9, aligned=True, shuffle=False,
+                        sampler_kw=dict(centerbias_weight=0.0, diff_weight=0.6, uniform_weight=0.1, grid_type=1))  # GRID_TYPE_PERTURBED
     correlations_case()
     sampler_draws_case()
     load_from_case()

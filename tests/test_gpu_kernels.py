@@ -554,3 +554,88 @@ def test_tensor_map_cache_is_hit_in_steady_state(ctx):
     torch.cuda.synchronize()
     h1, m1 = ctx.tensor_map_stats()
     assert m1 == m0 and h1 - h0 == 9      # three descriptors per launch, all from the cache
+
+
+# ---- the non-default branches of get_iqa_patches (patch_sampling.py:506-508, :530-531/:561, :46-222/:603-605) ----
+class _ReplaySampler:
+    """Stands in for the reference's PatchSampler on a box without the reference: returns the draws the real sampler
+    made when the fixture was generated (tests/golden/make_golden.py::patches_branch_case) and records the weight map
+    it is handed at every draw."""
+
+    def __init__(self, draws, diff0=None):
+        self.draws, self.diff0, self.seen, self.i = list(draws), diff0, [], 0
+
+    def compute_diff(self, imgs):
+        return None if self.diff0 is None else np.array(self.diff0, copy=True)
+
+    def get_sample_params(self, h, w, ho, wo, diff=None, num_samples=1, debug=False):
+        self.seen.append(None if diff is None else np.array(diff, copy=True))
+        d = self.draws[self.i]
+        self.i += 1
+        assert d.shape == (2, num_samples), (d.shape, num_samples)
+        return d
+
+
+def _branch_fixture(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, f"patches_{name}.npz"))
+    tens = [synth.to_tensor_normalized(g["ref_u8"]).cuda(), synth.to_tensor_normalized(g["dist_u8"]).cuda()]
+    draws = [g[f"draw_{i}"] for i in range(int(g["n_draws"]))]
+    return g, tens, draws
+
+
+def test_get_iqa_patches_unaligned_matches_reference(golden_dir):
+    """use_aligned_patches=False: ref and dist get their own coordinate sets (two draws per level)."""
+    from vtamiq_b200 import get_iqa_patches
+    g, tens, draws = _branch_fixture(golden_dir, "unaligned")
+    smp = _ReplaySampler(draws)
+    patches, pos, scales = get_iqa_patches((g["ref_u8"], g["dist_u8"]), tens, int(g["N"]), 16, smp,
+                                           int(g["n_scales_requested"]), scale_num_samples_ratio=float(g["ratio"]),
+                                           use_aligned_patches=False, random_seed=int(g["seed"]))
+    torch.cuda.synchronize()
+    assert smp.i == len(draws) == 4
+    assert np.array_equal(patches.cpu().numpy().view(np.uint32), g["patches"].view(np.uint32))
+    assert np.array_equal(pos.cpu().numpy().view(np.uint32), g["pos"].view(np.uint32))
+    assert np.array_equal(scales.cpu().numpy(), g["scales"])
+    assert not np.array_equal(g["pos"][0], g["pos"][1])      # the two images really use different positions
+
+
+def test_get_iqa_patches_difference_weighted_matches_reference(golden_dir):
+    """Difference-weighted sampler: compute_diff's map reaches the sampler at level 0 and, 2x mean-pooled, at level 1
+    (bit-identical to the reference's pooling); extraction bit-exact."""
+    from vtamiq_b200 import get_iqa_patches
+    g, tens, draws = _branch_fixture(golden_dir, "weighted")
+    smp = _ReplaySampler(draws, diff0=g["diff0"])
+    patches, pos, scales = get_iqa_patches((g["ref_u8"], g["dist_u8"]), tens, int(g["N"]), 16, smp,
+                                           int(g["n_scales_requested"]), scale_num_samples_ratio=float(g["ratio"]),
+                                           random_seed=int(g["seed"]))
+    torch.cuda.synchronize()
+    assert len(smp.seen) == 2
+    for i, w in enumerate(smp.seen):
+        assert w.dtype == g[f"weight_{i}"].dtype and np.array_equal(w, g[f"weight_{i}"])
+    assert np.array_equal(patches.cpu().numpy().view(np.uint32), g["patches"].view(np.uint32))
+    assert np.array_equal(pos.cpu().numpy().view(np.uint32), g["pos"].view(np.uint32))
+    assert np.array_equal(scales.cpu().numpy(), g["scales"])
+
+
+def test_get_iqa_patches_random_slot_order(golden_dir):
+    """randomize_patch_scale_order=True: slot perm[i] receives the i-th patch of the scale-ordered sequence, perm =
+    the first thing drawn from numpy's RNG after seeding (patch_sampling.py:506-508, :587-590).  The reference itself
+    raises on this branch under torch 2.11 (index_put of float64 into float32, :534), so the expectation is the
+    scale-ordered result of the same draws, permuted."""
+    from vtamiq_b200 import get_iqa_patches
+    g = np.load(os.path.join(golden_dir, "patches_multi3.npz"))
+    tens = [synth.to_tensor_normalized(g["ref_u8"]).cuda(), synth.to_tensor_normalized(g["dist_u8"]).cuda()]
+    draws = [g[f"samples_{i}"] for i in range(int(g["n_levels"]))]
+    N, seed = int(g["N"]), 31
+    args = ((g["ref_u8"], g["dist_u8"]), tens, N, 16)
+    kw = dict(scale_num_samples_ratio=float(g["ratio"]), random_seed=seed)
+    plain = get_iqa_patches(*args, _ReplaySampler(draws), int(g["n_scales_requested"]), **kw)
+    mixed = get_iqa_patches(*args, _ReplaySampler(draws), int(g["n_scales_requested"]),
+                            randomize_patch_scale_order=True, **kw)
+    torch.cuda.synchronize()
+    perm = np.random.RandomState(seed).permutation(N)
+    for a, b in zip(plain, mixed):
+        a, b = a.cpu().numpy(), b.cpu().numpy()
+        assert np.array_equal(b[:, perm], a)
+    assert not np.array_equal(mixed[2].cpu().numpy(), plain[2].cpu().numpy())   # scale ids are no longer sorted
+    assert np.array_equal(plain[0].cpu().numpy().view(np.uint32), g["patches"].view(np.uint32))

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvtamiq_b200.so")
 STAMP = LIB + ".stamp"
-SOURCES = ["api.cu", "gemm.cu", "attention.cu", "attention_v3.cu", "attention_v5.cu", "rowwise.cu", "gather.cu", "diffnet.cu", "tail_train.cu"]
+SOURCES = ["api.cu", "gemm.cu", "attention.cu", "attention_v3.cu", "attention_v5.cu", "rowwise.cu", "gather.cu", "diffnet.cu", "diffnet_cluster.cu", "tail_train.cu"]
 HEADERS = ["common.cuh", "host.h", os.path.join("..", "..", "include", "vtamiq_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

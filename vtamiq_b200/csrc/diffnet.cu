@@ -366,6 +366,10 @@ extern "C" int vtq_diffnet_head(vtq_ctx* ctx, const float* diff, const void* con
   VTQ_CHECK_ARG(ctx, diff && params && q && workspace, "null pointer");
   if (int rc = check_tail_args(ctx, params, n_params, num_rgs, num_rcabs, hidden, ca_hidden, head_hidden, B)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (diffnet_cluster_eligible(ctx, hidden, ca_hidden, head_hidden)) {  // the fast path: one launch of 16-CTA clusters
+    const int rc = launch_diffnet_cluster(ctx, diff, params, num_rgs, num_rcabs, hidden, ca_hidden, head_hidden, B, q, st);
+    if (rc <= 0) return rc;  // 1: clusters of that size cannot be scheduled here -> cooperative kernel below
+  }
   const size_t plane = static_cast<size_t>(B) * hidden;
   unsigned* counters = static_cast<unsigned*>(workspace);        // first 32 KB: barrier counters
   float* xbuf = reinterpret_cast<float*>(static_cast<char*>(workspace) + 32768);

@@ -29,6 +29,7 @@ struct vtq_ctx {
   std::unordered_set<const void*> smem_configured;
   std::unordered_map<std::string, CUtensorMap> tensor_maps;
   unsigned long long tensor_map_hits = 0, tensor_map_misses = 0;
+  int diffnet_max_clusters = 0;   // co-resident 16-CTA clusters of the DiffNet kernel (0 = not asked yet, -1 = none)
   int* oob_flag_host = nullptr;  // pinned + mapped: gather kernels set it when a coordinate is out of range
   int* oob_flag_dev = nullptr;
 };
@@ -140,6 +141,11 @@ TailSaved tail_saved_layout(int B, int num_rgs, int num_rcabs, int hidden, int c
 int launch_tail_train_forward(vtq_ctx* ctx, const float* d_scaled_in_saved, const void* const* params, int n_params,
                               int num_rgs, int num_rcabs, int hidden, int ca_hidden, int head_hidden, int B,
                               const float* drop_scale, float* saved, float* q, unsigned* counters, cudaStream_t st);
+// DiffNet + head on 16-CTA clusters (diffnet_cluster.cu); launch returns 1 when clusters of that size cannot be
+// scheduled on this device (the caller then uses the cooperative kernel)
+bool diffnet_cluster_eligible(const vtq_ctx* ctx, int hidden, int ca_hidden, int head_hidden);
+int launch_diffnet_cluster(vtq_ctx* ctx, const float* diff, const void* const* params, int num_rgs, int num_rcabs,
+                           int hidden, int ca_hidden, int head_hidden, int B, float* q, cudaStream_t st);
 int launch_attention(vtq_ctx* ctx, const void* qkv, void* out, int n_seq, int S, int heads, int dtype,
                      int q_rows, cudaStream_t st, long long* trace = nullptr);
 

@@ -261,7 +261,7 @@ def extract_patches(tensors: torch.Tensor, samples, patch_dim: int = 16, with_sc
     """Reference-format outputs for K images sharing one coordinate set (aligned patches).
 
     tensors : (K, 3, H, W) fp32 CUDA tensor (K=2 for FR-IQA: ref, dist)
-    samples : list over scales of float64 arrays/tensors (2, n_s)
+    samples : list over scales of float64 arrays/tensors (2, n_s), or (K, 2, n_s) = one coordinate set per image
     returns (patches (K,N,3,P,P) fp32, pos (K,N,2) fp32, scales (K,N) int32 | None) — bit-identical to
     ``get_iqa_patches(...)`` run with the same coordinates.
     """
@@ -277,7 +277,12 @@ def extract_patches(tensors: torch.Tensor, samples, patch_dim: int = 16, with_sc
         tensors = tensors.to(torch.float32).contiguous()
     K = tensors.shape[0]
     dev = tensors.device
-    smp = [torch.as_tensor(np.asarray(s), dtype=torch.float64).to(dev).reshape(1, 2, -1).contiguous() for s in samples]
+    # one coordinate set shared by all images: (2, n_s); or one set per image (unaligned patches): (K, 2, n_s)
+    smp = [torch.as_tensor(np.asarray(s), dtype=torch.float64).to(dev) for s in samples]
+    smp = [(s.reshape(1, 2, -1) if s.dim() == 2 else s).contiguous() for s in smp]
+    for s in smp:
+        if s.dim() != 3 or s.shape[1] != 2 or s.shape[0] not in (1, K):
+            raise ValueError("samples[s] must be (2, n_s) or (K, 2, n_s)")
     N = int(sum(s.shape[-1] for s in smp))
     use_scales = (len(smp) > 1) if with_scales is None else with_scales
     patches = torch.zeros(K, N, 3, patch_dim, patch_dim, dtype=torch.float32, device=dev)
@@ -290,12 +295,12 @@ def extract_patches(tensors: torch.Tensor, samples, patch_dim: int = 16, with_sc
         n = sm.shape[-1]
         if lvl is None:
             H, W = tensors.shape[1], tensors.shape[2]
-            ctx.call("vtq_patch_gather_u8", _ptr(tensors), K, H, W, _ptr(sm), 1, n, off, N, _ptr(patches), None,
-                     VTQ_F16, _ptr(pos), _ptr(scales), s, _stream(dev))
+            ctx.call("vtq_patch_gather_u8", _ptr(tensors), K, H, W, _ptr(sm), sm.shape[0], n, off, N, _ptr(patches),
+                     None, VTQ_F16, _ptr(pos), _ptr(scales), s, _stream(dev))
         else:
             H, W = lvl.shape[-2:]
-            ctx.call("vtq_patch_gather", _ptr(lvl), K, H, W, _ptr(sm), 1, n, off, N, _ptr(patches), None, VTQ_F16,
-                     _ptr(pos), _ptr(scales), s, _stream(dev))
+            ctx.call("vtq_patch_gather", _ptr(lvl), K, H, W, _ptr(sm), sm.shape[0], n, off, N, _ptr(patches), None,
+                     VTQ_F16, _ptr(pos), _ptr(scales), s, _stream(dev))
         off += n
     check_coordinates(ctx, sync=True)   # reference-format API: raise for THIS call, like the reference does
     return patches, pos, (scales.to(torch.int32) if use_scales else None)
@@ -304,13 +309,16 @@ def extract_patches(tensors: torch.Tensor, samples, patch_dim: int = 16, with_sc
 def get_iqa_patches(imgs, tensors, patch_count, patch_dim, patch_sampler, patch_num_scales,
                     scale_num_samples_ratio=DEFAULT_NUM_SAMPLES_RATIO, use_aligned_patches=True,
                     randomize_patch_scale_order=False, random_seed=None, debug=False):
-    """Same call signature as the reference function (patch_sampling.py:450-461).  ``patch_sampler`` is the
-    reference's own ``PatchSampler`` (or any object with ``compute_diff`` / ``get_sample_params``): it still
-    chooses the coordinates on the host with numpy's RNG; extraction happens on the GPU.
-    Only the shipped configuration is accelerated: aligned patches, scale-ordered output."""
-    if not use_aligned_patches or randomize_patch_scale_order:
-        raise NotImplementedError("vtamiq_b200.get_iqa_patches: only use_aligned_patches=True and "
-                                  "randomize_patch_scale_order=False are on the accelerated path")
+    """Same call signature and outputs as the reference function (patch_sampling.py:450-613).  ``patch_sampler`` is
+    the reference's own ``PatchSampler`` (or any object with ``compute_diff`` / ``get_sample_params``): it still
+    chooses the coordinates on the host with numpy's RNG, consumed in the reference's order (slot permutation first,
+    :506-508; then per level one draw, or one draw per image when ``use_aligned_patches=False``, :561); the
+    difference-weighted modes get their weight map mean-pooled per level exactly like :603-605.  Extraction, uv and
+    scale ids happen on the GPU (one coordinate set per image when patches are not aligned); the reference's random
+    slot order (``randomize_patch_scale_order``) is a device-side permutation of the scale-ordered result."""
+    if debug:
+        raise NotImplementedError("vtamiq_b200.get_iqa_patches: debug=True changes the meaning of pos / scales "
+                                  "(patch_sampling.py:569-583) and is not supported")
     if len(imgs) != len(tensors):
         raise ValueError("get_iqa_patches(): Image and Tensor counts should match.")
     if patch_count < patch_num_scales:
@@ -322,23 +330,40 @@ def get_iqa_patches(imgs, tensors, patch_count, patch_dim, patch_sampler, patch_
     try:
         ref = imgs[0]
         height, width = (ref.height, ref.width) if hasattr(ref, "height") else ref.shape[:2]
+        patch_indices = np.random.permutation(patch_count) if randomize_patch_scale_order else None
         diff = patch_sampler.compute_diff(imgs)
-        if diff is not None:
-            # difference-weighted sampling pools the weight map per level on the host; the shipped
-            # configuration (GRID_TYPE_PERTURBED_SIMPLE, patch_sampling.py:65-69) never produces one
-            raise NotImplementedError("vtamiq_b200.get_iqa_patches: difference-weighted sampling is not accelerated")
         n_scales = compute_patch_num_scales(patch_num_scales, height, width, patch_dim, patch_dim)
         counts = compute_num_patches_per_scale(patch_count, n_scales, scale_num_samples_ratio)
         t = torch.stack(list(tensors), dim=0)
+        n_sets = 1 if use_aligned_patches else len(imgs)
         samples, h, w, total = [], t.shape[-2], t.shape[-1], 0
         for s in range(n_scales):
             n_s = int(counts[-s - 1])
-            samples.append(patch_sampler.get_sample_params(h, w, patch_dim, patch_dim, diff=diff, num_samples=n_s))
+            draws = [patch_sampler.get_sample_params(h, w, patch_dim, patch_dim, diff=diff, num_samples=n_s)
+                     for _ in range(n_sets)]
+            samples.append(np.stack([np.asarray(d, dtype=np.float64) for d in draws]))   # (n_sets, 2, n_s)
             h, w = h // 2, w // 2
+            if diff is not None:   # the weight map follows the image pyramid (host side, like the sampler itself)
+                d = torch.as_tensor(diff)
+                diff = torch.nn.functional.avg_pool2d(d.view(1, 1, *d.shape), 2).squeeze().numpy()
             total += n_s
             if patch_count <= total:
                 break
     finally:
         if state is not None:
             np.random.set_state(state)
-    return extract_patches(t, samples, patch_dim, with_scales=n_scales > 1)
+    patches, pos, scales = extract_patches(t, samples, patch_dim, with_scales=n_scales > 1)
+    if total < patch_count:   # the pyramid ran out of levels: the reference leaves the remaining slots zero
+        pad = patch_count - total
+        patches = torch.cat([patches, patches.new_zeros(patches.shape[0], pad, *patches.shape[2:])], dim=1)
+        pos = torch.cat([pos, pos.new_zeros(pos.shape[0], pad, 2)], dim=1)
+        if scales is not None:
+            scales = torch.cat([scales, scales.new_zeros(scales.shape[0], pad)], dim=1)
+    if patch_indices is not None:
+        # slot patch_indices[i] receives the i-th patch of the scale-ordered sequence (:587-590)
+        perm = torch.as_tensor(patch_indices[:patches.shape[1]], dtype=torch.long, device=patches.device)
+        patches = torch.empty_like(patches).index_copy_(1, perm, patches)
+        pos = torch.empty_like(pos).index_copy_(1, perm, pos)
+        if scales is not None:
+            scales = torch.empty_like(scales).index_copy_(1, perm, scales)
+    return patches, pos, scales
