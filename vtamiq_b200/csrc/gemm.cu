@@ -42,6 +42,11 @@ constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_STAGING_BYTES = GEMM_EPI_WARPS * 4096;  // one 32-row x 128 B staging box per epilogue warp
 constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;
 
+#ifndef VTQ_GEMM_F32_NBUF
+#define VTQ_GEMM_F32_NBUF 1   // staging boxes per epilogue warp of the fp32 (residual) epilogue.  2 (two boxes, one pipeline
+                              // stage less) measured slower: out-proj 0.060 -> 0.064 ms, fc2 0.146 -> 0.154 ms (r02 notes)
+#endif
+
 enum : int { EPI_H = 0, EPI_F32 = 1 };
 enum : int { LN_NONE = 0, LN_CONSUME = 1, LN_PRODUCE = 2 };
 
@@ -98,15 +103,19 @@ __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
 // (`half` = 0/1: the two warps sharing a lane quarter interleave chunks).  The caller signals "accumulator free"
 // after this returns (all TMEM reads of the warp are complete by then).
 // ------------------------------------------------------------------------------------------------
-template <int DT, int BN, int EPI, bool GELU, int LN = LN_NONE>
+template <int DT, int BN, int EPI, bool GELU, int LN = LN_NONE, int NBUF = 1>
 __device__ __forceinline__ void epilogue_tile(uint32_t t_row, int row0, int n0, int N, const float* __restrict__ bias,
                                               const float* __restrict__ gamma, int accumulate,
-                                              const CUtensorMap* tmO, uint8_t* buf, int lane, int half,
+                                              const CUtensorMap* tmO, uint8_t* buf0, int lane, int half,
                                               uint64_t hint_o, const float* __restrict__ colsum = nullptr,
-                                              float ln_a = 1.f, float ln_b = 0.f) {
+                                              float ln_a = 1.f, float ln_b = 0.f, uint32_t* box_counter = nullptr) {
   const uint32_t swz = static_cast<uint32_t>(lane & 7);
   if constexpr (EPI == EPI_F32) {
-    // 32 fp32 columns (128 B per row) per staged box
+    // 32 fp32 columns (128 B per row) per staged box.  NBUF = 2: the warp alternates between two boxes, so staging
+    // chunk i+1 only waits for the store / reduce-add of chunk i-1 to have read its box — with one box every chunk
+    // waits out the full latency of the previous bulk reduce (the K = 768 residual GEMM was epilogue-latency bound).
+    uint32_t local_counter = 0;
+    uint32_t& bc = (NBUF == 2 && box_counter != nullptr) ? *box_counter : local_counter;
 #pragma unroll 1
     for (int c = half; c < BN / 32; c += 2) {
       const int ncol = n0 + c * 32;
@@ -114,7 +123,14 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_row, int row0, int n0, 
       uint32_t r[32];
       tmem_ld32(t_row + c * 32, r);
       tmem_wait_ld();
-      if (lane == 0) tma_wait_group_read<0>();  // the previous store has finished reading the staging box
+      uint8_t* buf = buf0;
+      if constexpr (NBUF == 2) {
+        buf = buf0 + (bc & 1) * 4096;
+        ++bc;
+        if (lane == 0) tma_wait_group_read<1>();  // the store before the previous one has finished reading this box
+      } else {
+        if (lane == 0) tma_wait_group_read<0>();  // the previous store has finished reading the staging box
+      }
       __syncwarp();
       const uint32_t row_addr = smem_u32(buf) + lane * 128;
 #pragma unroll
@@ -147,6 +163,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_row, int row0, int n0, 
       if (ncol >= N) break;
       if (lane == 0) tma_wait_group_read<0>();
       __syncwarp();
+      uint8_t* buf = buf0;
       const uint32_t row_addr = smem_u32(buf) + lane * 128;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
@@ -503,13 +520,17 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
 }
 
-template <int BN, int LN>
+template <int BN, int LN, int EPI = EPI_H>
 struct Gemm2Cfg {
   static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;  // this CTA's half of the W tile
   static constexpr int STAGE_BYTES = GEMM_A_BYTES + B_BYTES;
+  // fp32 epilogue (store / reduce-add into the residual stream) without LayerNorm folding: two staging boxes per warp
+  static constexpr int NBUF = (EPI == EPI_F32 && LN == LN_NONE) ? VTQ_GEMM_F32_NBUF : 1;
   // LN_PRODUCE adds a 2 KB 16-bit staging box per epilogue warp (behind the 4 KB fp32 boxes)
-  static constexpr int STAGING_BYTES = GEMM_STAGING_BYTES + (LN == LN_PRODUCE ? GEMM_EPI_WARPS * 2048 : 0);
-  static constexpr int STAGES = (LN == LN_PRODUCE) ? ((BN == 128) ? 7 : (BN == 192 ? 6 : 5)) : ((BN == 128) ? 8 : 6);
+  static constexpr int STAGING_BYTES = NBUF * GEMM_STAGING_BYTES + (LN == LN_PRODUCE ? GEMM_EPI_WARPS * 2048 : 0);
+  static constexpr int STAGES = (LN == LN_PRODUCE) ? ((BN == 128) ? 7 : (BN == 192 ? 6 : 5))
+                                : (NBUF == 2)      ? ((BN == 128) ? 6 : (BN == 192 ? 5 : 4))
+                                                   : ((BN == 128) ? 8 : 6);
   static constexpr int ACC_STRIDE = (BN > 128) ? 256 : 128;
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256;
@@ -523,7 +544,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
                  const float* __restrict__ bias, const float* __restrict__ gamma, int M, int N, int K, int accumulate,
                  uint64_t hint_a, uint64_t hint_o, const LnFold ln) {
-  using Cfg = Gemm2Cfg<BN, LN>;
+  using Cfg = Gemm2Cfg<BN, LN, EPI>;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* ring = smem;
@@ -621,7 +642,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     // ------------------------------- epilogue (both CTAs, own 128 rows) ----------
     const int lane_grp = warp & 3;
     const int half = (warp - 2) >> 2;
-    uint8_t* my_staging = staging + (warp - 2) * 4096;
+    uint8_t* my_staging = staging + (warp - 2) * 4096 * Cfg::NBUF;
+    uint32_t box_counter = 0;  // staging boxes this warp has filled (NBUF == 2: box = counter & 1)
     uint32_t it = 0;
     for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
       const int m0 = (t / num_n) * (2 * GEMM_BM) + static_cast<int>(rank) * GEMM_BM;
@@ -658,8 +680,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
         epilogue_resid_ln<DT, BN>(t_row, row_ok, m0 + lane_grp * 32, n0, N, bias, gamma, &tmO, &tmR, my_staging, my_raw,
                                   stats, half, lane, xp);
       } else {
-        epilogue_tile<DT, BN, EPI, GELU, LN>(t_row, m0 + lane_grp * 32, n0, N, bias, gamma, accumulate, &tmO,
-                                             my_staging, lane, half, hint_o, ln.colsum, ln_a, ln_b);
+        epilogue_tile<DT, BN, EPI, GELU, LN, Cfg::NBUF>(t_row, m0 + lane_grp * 32, n0, N, bias, gamma, accumulate,
+                                                        &tmO, my_staging, lane, half, hint_o, ln.colsum, ln_a, ln_b,
+                                                        &box_counter);
       }
       tc_fence_before();
       __syncwarp();
@@ -696,7 +719,7 @@ template <int DT, int BN, int EPI, bool GELU, int LN>
 static int launch_2cta(vtq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
                        const CUtensorMap& tmR, const float* bias, const float* gamma, int M, int N, int K,
                        int accumulate, uint64_t hint_a, uint64_t hint_o, const LnFold& ln, cudaStream_t st) {
-  using Cfg = Gemm2Cfg<BN, LN>;
+  using Cfg = Gemm2Cfg<BN, LN, EPI>;
   auto kern = gemm2_kernel<DT, BN, EPI, GELU, LN>;
   if (int rc = ensure_dyn_smem(ctx, kern, Cfg::SMEM_BYTES, "gemm2: cudaFuncSetAttribute")) return rc;
   const int num_tiles = ((M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * ((N + BN - 1) / BN);
