@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VTQ_ABI_VERSION 3
+#define VTQ_ABI_VERSION 4
 
 enum vtq_status {
   VTQ_OK = 0,
@@ -90,6 +90,16 @@ int vtq_patch_gather(vtq_ctx* ctx, const float* images, int n_img, int H, int W,
 int vtq_patch_gather_u8(vtq_ctx* ctx, const uint8_t* images, int n_img, int H, int W, const double* samples, int n_set,
                         int n, int patch_offset, int N_total, float* patches_f32, void* patches_16, int dtype,
                         float* pos, float* scales, int scale_id, void* stream);
+
+/* Coordinate sampler on the device (SURVEY 8f "next" #3): the law of the reference's default sampler,
+ * PatchSampler(grid_type=GRID_TYPE_PERTURBED_SIMPLE) -> stratified_grid_sampling (data/patch_sampling.py:236-237,
+ * :308-327, :362-376), for `batch` images in one launch: n DISTINCT points of the height x width grid
+ * (width = ceil(sqrt(n / (h/w))), height = ceil(width * h/w)) chosen uniformly, jittered by U(-2a, 2a) cells, clipped,
+ * scaled to [0, h-ho] x [0, w-wo].  key2: two 64-bit words ON THE DEVICE (the caller draws them with its own
+ * generator; Philox4x32-10 is keyed by them).  out [batch][2][n] float64, row 0 = y — the layout vtq_patch_gather takes.
+ * Parity with numpy's RNG stream is statistical by necessity (tests/golden/sampler_draws.npz). */
+int vtq_sample_grid(vtq_ctx* ctx, const void* key2, int batch, int h, int w, int ho, int wo, int n,
+                    double perturbed_amount, double* out, void* stream);
 
 /* The same transform for whole images: uint8 [n_img][H][W][3] -> fp32 [n_img][3][H][W]. */
 int vtq_normalize_u8(vtq_ctx* ctx, const uint8_t* src, float* dst, int n_img, int H, int W, void* stream);

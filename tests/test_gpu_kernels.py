@@ -639,3 +639,42 @@ def test_get_iqa_patches_random_slot_order(golden_dir):
         assert np.array_equal(b[:, perm], a)
     assert not np.array_equal(mixed[2].cpu().numpy(), plain[2].cpu().numpy())   # scale ids are no longer sorted
     assert np.array_equal(plain[0].cpu().numpy().view(np.uint32), g["patches"].view(np.uint32))
+
+
+def test_device_sampler_kernel_has_the_reference_law(golden_dir):
+    """vtq_sample_grid (one launch per level, Philox-keyed permutation of the grid cells + jitter) against raw draws of
+    the reference's default sampler (tests/golden/sampler_draws.npz): same support, one sample per distinct grid cell,
+    same jitter range, marginals a two-sample KS test cannot separate; reproducible from the generator state."""
+    import scipy.stats
+    from vtamiq_b200.patch_sampling import perturbed_grid_samples, sample_batch
+    z = np.load(os.path.join(golden_dir, "sampler_draws.npz"))
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for name in ("cfg2", "small", "tall"):
+        ref = z[name].astype(np.float64)                       # (draws, 2, n)
+        h, w, n = (int(v) for v in z[name + "_hwn"])
+        ours = perturbed_grid_samples(ref.shape[0], h, w, 16, 16, n, device="cuda", generator=g).cpu().numpy()
+        assert ours.shape == ref.shape and ours.dtype == np.float64
+        width = max(int(np.ceil(np.sqrt(n / (h / w)))), 1)
+        height = int(np.ceil(width * h / w))
+        for smp in (ours, ref):
+            assert smp[:, 0].min() >= 0 and smp[:, 0].max() <= h - 16 and smp[:, 1].min() >= 0 and smp[:, 1].max() <= w - 16
+            cy = np.minimum(np.floor(smp[:, 0] / (h - 16) * height), height - 1)
+            cx = np.minimum(np.floor(smp[:, 1] / (w - 16) * width), width - 1)
+            cell = (cy * width + cx).astype(int)
+            assert all(len(set(row)) == n for row in cell)     # n distinct grid cells per image
+            off_y = smp[:, 0] / (h - 16) * height - cy - 0.5   # jitter inside the cell, |.| <= 2 * 0.2
+            off_x = smp[:, 1] / (w - 16) * width - cx - 0.5
+            assert np.abs(off_y).max() <= 0.4 + 1e-6 and np.abs(off_x).max() <= 0.4 + 1e-6
+        for axis in (0, 1):
+            p = scipy.stats.ks_2samp(ours[:, axis].ravel(), ref[:, axis].ravel()).pvalue
+            assert p > 1e-3, (name, axis, p)
+        # images of one batch get different draws; the same generator state reproduces the batch
+        assert not np.array_equal(ours[0], ours[1])
+    a = perturbed_grid_samples(4, 384, 512, 16, 16, 500, device="cuda", generator=torch.Generator(device="cuda").manual_seed(9))
+    b = perturbed_grid_samples(4, 384, 512, 16, 16, 500, device="cuda", generator=torch.Generator(device="cuda").manual_seed(9))
+    assert torch.equal(a, b)
+    levels = sample_batch(3, 1024, 1024, 500, 16, 3, 2.0, device="cuda", generator=g)
+    assert [tuple(t.shape) for t in levels] == [(3, 2, 380), (3, 2, 96), (3, 2, 24)]
+    assert float(levels[2][:, 0].max()) <= 256 - 16
+    big = perturbed_grid_samples(2, 2160, 3840, 16, 16, 5000, device="cuda", generator=g)      # cfg4: 8192-key sort
+    assert big.shape == (2, 2, 5000) and float(big[:, 0].max()) <= 2160 - 16 and float(big[:, 1].max()) <= 3840 - 16

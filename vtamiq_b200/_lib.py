@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("VTQ_LIBRARY") or os.path.join(_HERE, "libvtamiq_b200.
 
 VTQ_F16, VTQ_BF16 = 0, 1
 EPI_BIAS_H, EPI_BIAS_GELU_H, EPI_BIAS_F32, EPI_BIAS_RESID_F32 = 0, 1, 2, 3
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
@@ -33,6 +33,7 @@ SIGNATURES = {
     "vtq_coord_status": (_i, [_vp, _i]),
     "vtq_tensor_map_stats": (_i, [_vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     "vtq_normalize_u8": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "vtq_sample_grid": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, C.c_double, _vp, _vp]),
     "vtq_avgpool2x2": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "vtq_cast_rows": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
     "vtq_embed_assemble": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),

@@ -457,6 +457,82 @@ static bool force_scalar_gather() {
 // ================================================================================================
 using namespace vtq;
 
+
+// ------------------------------------------------------------------------------------------------
+// Coordinate sampler (SURVEY 8f "next" #3): the reference's default law, PatchSampler(GRID_TYPE_PERTURBED_SIMPLE) ->
+// stratified_grid_sampling (data/patch_sampling.py:236-237, :308-327, :362-376), for a whole batch on the device.
+// One block per image: a uniform random permutation of the `height x width` grid cells (64-bit keys = 32 random bits |
+// cell index, bitonic sort in shared memory), the first n cells are the image's n DISTINCT grid points; each is
+// jittered by U(-2a, 2a) cells, moved to the cell centre, clipped to [0, 1] and scaled to [0, h-ho] x [0, w-wo].
+// Randomness: Philox4x32-10 keyed by two 64-bit words the caller drew with its own generator (read on the device).
+// ------------------------------------------------------------------------------------------------
+namespace vtq {
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ double u01_53(uint32_t hi, uint32_t lo) {  // uniform in [0, 1) with 53 random bits
+  const unsigned long long v = ((static_cast<unsigned long long>(hi) << 32) | lo) >> 11;
+  return static_cast<double>(v) * (1.0 / 9007199254740992.0);
+}
+
+__global__ void __launch_bounds__(256) sample_grid_kernel(const unsigned long long* __restrict__ key, int h, int w, int ho,
+                                                          int wo, int n, int height, int width, int padded,
+                                                          double amount, double* __restrict__ out) {
+  extern __shared__ unsigned long long sg_keys[];  // [padded]
+  const int img = blockIdx.x;
+  const int cells = height * width;
+  const uint32_t k0 = static_cast<uint32_t>(key[0]), k1 = static_cast<uint32_t>(key[0] >> 32);
+  const uint32_t s0 = static_cast<uint32_t>(key[1]), s1 = static_cast<uint32_t>(key[1] >> 32);
+  for (int c = threadIdx.x; c < padded; c += blockDim.x) {
+    unsigned long long v = ~0ull;
+    if (c < cells) {
+      uint32_t r[4];
+      philox4x32_10(static_cast<uint32_t>(c), static_cast<uint32_t>(img), s0, s1 ^ 0x5A17u, k0, k1, r);
+      v = (static_cast<unsigned long long>(r[0]) << 32) | static_cast<uint32_t>(c);
+    }
+    sg_keys[c] = v;
+  }
+  __syncthreads();
+  for (int k = 2; k <= padded; k <<= 1) {       // bitonic sort, ascending
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < padded; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = sg_keys[i], b = sg_keys[ixj];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) { sg_keys[i] = b; sg_keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  double* oy = out + static_cast<size_t>(img) * 2 * n;
+  double* ox = oy + n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = static_cast<int>(sg_keys[i] & 0xffffffffull);
+    const double gy = static_cast<double>(c % height);  // the reference flattens its (2, width, height) grid this way
+    const double gx = static_cast<double>(c / height);
+    uint32_t r[4];
+    philox4x32_10(static_cast<uint32_t>(i), static_cast<uint32_t>(img), s0, s1 ^ 0xC0FFEEu, k0, k1, r);
+    const double jy = (2.0 * u01_53(r[0], r[1]) - 1.0) * (2.0 * amount);
+    const double jx = (2.0 * u01_53(r[2], r[3]) - 1.0) * (2.0 * amount);
+    const double py = fmin(fmax((gy + jy) / height + 0.5 / height, 0.0), 1.0);
+    const double px = fmin(fmax((gx + jx) / width + 0.5 / width, 0.0), 1.0);
+    oy[i] = py * (h - ho);
+    ox[i] = px * (w - wo);
+  }
+}
+}  // namespace vtq
+
 extern "C" int vtq_patch_gather(vtq_ctx* ctx, const float* images, int n_img, int H, int W, const double* samples,
                                 int n_set, int n, int patch_offset, int N_total, float* patches_f32,
                                 void* patches_16, int dtype, float* pos, float* scales, int scale_id,
@@ -582,5 +658,27 @@ extern "C" int vtq_avgpool2x2_u8(vtq_ctx* ctx, const uint8_t* src, float* dst, i
   avgpool2x2_u8_kernel<<<static_cast<unsigned>((total4 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src, dst, H, W, Ho, Wo, total4);
   VTQ_CHECK_LAUNCH(ctx, "avgpool2x2_u8 launch");
+  return VTQ_OK;
+}
+
+extern "C" int vtq_sample_grid(vtq_ctx* ctx, const void* key2, int batch, int h, int w, int ho, int wo, int n,
+                               double perturbed_amount, double* out, void* stream) {
+  VTQ_ENTER(ctx);
+  VTQ_CHECK_ARG(ctx, key2 && out, "null pointer");
+  VTQ_CHECK_ARG(ctx, batch >= 1 && n >= 1 && h > ho && w > wo && ho >= 1 && wo >= 1, "shape");
+  const double aspect = static_cast<double>(h) / static_cast<double>(w);
+  int width = static_cast<int>(ceil(sqrt(static_cast<double>(n) / aspect)));
+  if (width < 1) width = 1;
+  const int height = static_cast<int>(ceil(width * aspect));
+  const long long cells = static_cast<long long>(height) * width;
+  VTQ_CHECK_ARG(ctx, cells >= n, "grid smaller than the sample count");
+  int padded = 1;
+  while (padded < cells) padded <<= 1;
+  const int smem = padded * 8;
+  VTQ_CHECK_ARG(ctx, smem <= ctx->smem_optin, "too many samples per image for the shared-memory sort (n <= ~25000)");
+  if (int rc = vtq::ensure_dyn_smem(ctx, vtq::sample_grid_kernel, ctx->smem_optin, "sample_grid: cudaFuncSetAttribute")) return rc;
+  vtq::sample_grid_kernel<<<batch, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const unsigned long long*>(key2), h, w, ho, wo, n, height, width, padded, perturbed_amount, out);
+  VTQ_CHECK_LAUNCH(ctx, "sample_grid launch");
   return VTQ_OK;
 }

@@ -102,6 +102,22 @@ class _Workspace:
         self.graph = None      # captured encoder+tail graph
 
 
+class _WsView:
+    """Pointers into a workspace's row-indexed buffers, offset to a sequence range (patch row p0, token row r0)."""
+
+    def __init__(self, ws: _Workspace, p0: int, r0: int):
+        off = lambda t, rows: None if t is None else C.c_void_p(t.data_ptr() + rows * t.stride(0) * t.element_size())
+        self.patches16, self.proj, self.pos, self.scales = (off(ws.patches16, p0), off(ws.proj, p0), off(ws.pos, p0),
+                                                            off(ws.scales, p0))
+        self.x, self.ln, self.qkv, self.att, self.h1 = (off(ws.x, r0), off(ws.ln, r0), off(ws.qkv, r0), off(ws.att, r0),
+                                                        off(ws.h1, r0))
+        # statistics slots are [slot][row][2]: a row offset inside every slot (the kernels index slot * M + row with
+        # M = the rows of THEIR launch, so split launches are only used without LayerNorm folding)
+        self.stats = off(ws.stats.view(-1, 2), r0)
+        self.pos_idx = off(ws.pos_idx, p0)
+        self.scale_idx = off(ws.scale_idx, p0)
+
+
 class Engine:
     """Packed weights + workspaces + launch sequence for one VTAMIQ module on one device."""
 
@@ -128,6 +144,9 @@ class Engine:
         self.static_weights = False   # True: skip the per-forward parameter version walk (weights promised frozen)
         self.dump_indices = False
         self.timeline = None   # when a list: (tag, start_event, end_event) per launch (bench.py roofline leg)
+        # two kernel chains (halves of the sequence batch) on two streams inside the captured step: VTQ_SPLIT_STREAMS=1
+        self.split_streams = os.environ.get("VTQ_SPLIT_STREAMS", "0") == "1"
+        self._side_stream = None
 
     def _call(self, tag, name, *args):
         """ctx.call, optionally bracketed by CUDA events on the launching stream."""
@@ -282,24 +301,24 @@ class Engine:
         self._ws.clear()
 
     # ------------------------------------------------------------------ launch sequence
-    def _encode_and_score(self, ws: _Workspace, embedded: bool, tail: bool = True):
-        """Everything after the inputs sit in ws.patches16 / ws.proj, ws.pos, ws.scales.  ``tail=False`` stops after
-        the encoder with ws.diff = LN(cls_ref) - LN(cls_dist) (no diff_scale): the differentiable tail takes over."""
-        c, st, dt = self._call, _stream(self.device), self.vtq16
-        B, N, S, H = ws.B, ws.N, ws.S, self.hidden
-        n_seq, rows, prow = ws.streams * B, ws.streams * B * S, ws.streams * B * N
+    def _encode_part(self, ws: _Workspace, embedded: bool, seq0: int, n_seq: int, st):
+        """Patch projection, embedding and the encoder blocks for sequences [seq0, seq0 + n_seq) on stream ``st``."""
+        c, dt = self._call, self.vtq16
+        N, S, H = ws.N, ws.S, self.hidden
+        rows, prow = n_seq * S, n_seq * N
+        w = _WsView(ws, seq0 * N, seq0 * S)
         if not embedded:
-            c("gemm_embed", "vtq_gemm", _ptr(ws.patches16), 0, _ptr(self.w_pe), _ptr(self.b_pe), prow, H,
-              self.patch_elems, dt, EPI_BIAS_F32, _ptr(ws.proj), 0, None, st)
+            c("gemm_embed", "vtq_gemm", w.patches16, 0, _ptr(self.w_pe), _ptr(self.b_pe), prow, H,
+              self.patch_elems, dt, EPI_BIAS_F32, w.proj, 0, None, st)
         if self.dump_indices:
             if ws.pos_idx is None:
                 ws.pos_idx = torch.zeros(prow, dtype=torch.int32, device=self.device)
                 ws.scale_idx = torch.zeros(prow, dtype=torch.int32, device=self.device)
-        c("embed_assemble", "vtq_embed_assemble", _ptr(ws.proj), _ptr(ws.pos),
-          _ptr(ws.scales) if self.scale_table is not None else None,
+        c("embed_assemble", "vtq_embed_assemble", w.proj, w.pos,
+          w.scales if self.scale_table is not None else None,
           _ptr(self.pos_table), self.pos_grid, _ptr(self.scale_table), self.num_scales, _ptr(self.cls),
-          _ptr(self.extra), self.n_extra, n_seq, N, H, _ptr(ws.x),
-          _ptr(ws.pos_idx) if self.dump_indices else None, _ptr(ws.scale_idx) if self.dump_indices else None, st)
+          _ptr(self.extra), self.n_extra, n_seq, N, H, w.x,
+          w.pos_idx if self.dump_indices else None, w.scale_idx if self.dump_indices else None, st)
         eps = self.ln_eps
         n_layers = len(self.layers)
         # Folded LayerNorms: ws.ln holds the RAW 16-bit copy of x, ws.stats each row's (sum, sum of squares) partials;
@@ -307,52 +326,82 @@ class Engine:
         fold = self.fuse_layernorm and rows >= 256
         slots_in = 1
         if fold:
-            c("rowstats_cast", "vtq_rowstats_cast", _ptr(ws.x), rows, H, _ptr(ws.ln), _ptr(ws.stats), dt, st)
+            c("rowstats_cast", "vtq_rowstats_cast", w.x, rows, H, w.ln, w.stats, dt, st)
         for li, L in enumerate(self.layers):
             if fold:
-                c("gemm_qkv", "vtq_gemm_ln", _ptr(ws.ln), 0, _ptr(L.w_qkv_f), _ptr(L.b_qkv_f), rows, 3 * H, H, dt,
-                  EPI_BIAS_H, _ptr(ws.qkv), 0, None, _ptr(ws.stats), slots_in, _ptr(L.cs_qkv), eps, None, None, st)
+                c("gemm_qkv", "vtq_gemm_ln", w.ln, 0, _ptr(L.w_qkv_f), _ptr(L.b_qkv_f), rows, 3 * H, H, dt,
+                  EPI_BIAS_H, w.qkv, 0, None, w.stats, slots_in, _ptr(L.cs_qkv), eps, None, None, st)
             else:
-                c("layernorm", "vtq_layernorm", _ptr(ws.x), 0, _ptr(L.ln1_w), _ptr(L.ln1_b), eps, rows, H, _ptr(ws.ln),
+                c("layernorm", "vtq_layernorm", w.x, 0, _ptr(L.ln1_w), _ptr(L.ln1_b), eps, rows, H, w.ln,
                   dt, st)
-                c("gemm_qkv", "vtq_gemm", _ptr(ws.ln), 0, _ptr(L.w_qkv), _ptr(L.b_qkv), rows, 3 * H, H, dt, EPI_BIAS_H,
-                  _ptr(ws.qkv), 0, None, st)
+                c("gemm_qkv", "vtq_gemm", w.ln, 0, _ptr(L.w_qkv), _ptr(L.b_qkv), rows, 3 * H, H, dt, EPI_BIAS_H,
+                  w.qkv, 0, None, st)
             if self.prune_last_block and li == n_layers - 1:
                 # Only the quality token of each sequence survives the encoder (transformer.py:634, vtamiq.py:104-108):
                 # in the last block K/V still need every row, but attention output, out-projection, LayerNorm and the
                 # MLP are evaluated for that one row per sequence (row stride S*H picks it out of x / att).
                 tok = self.token_num
-                c("attention_tok", "vtq_attention_fwd", _ptr(ws.qkv), _ptr(ws.att), n_seq, S, self.heads, dt,
+                c("attention_tok", "vtq_attention_fwd", w.qkv, w.att, n_seq, S, self.heads, dt,
                   tok + 1, st)
-                x_tok = C.c_void_p(ws.x.data_ptr() + tok * H * 4)
-                att_tok = C.c_void_p(ws.att.data_ptr() + tok * H * 2)
+                x_tok = C.c_void_p(w.x.value + tok * H * 4)
+                att_tok = C.c_void_p(w.att.value + tok * H * 2)
                 c("gemm_out_tok", "vtq_gemm", att_tok, S * H, _ptr(L.w_o), _ptr(L.b_o), n_seq, H, H, dt,
                   EPI_BIAS_RESID_F32, x_tok, S * H, _ptr(L.g1), st)
                 c("layernorm_tok", "vtq_layernorm", x_tok, S * H, _ptr(L.ln2_w), _ptr(L.ln2_b), eps, n_seq, H,
-                  _ptr(ws.ln), dt, st)
-                c("gemm_fc1_tok", "vtq_gemm", _ptr(ws.ln), 0, _ptr(L.w_fc1), _ptr(L.b_fc1), n_seq, self.mlp_dim, H, dt,
-                  EPI_BIAS_GELU_H, _ptr(ws.h1), 0, None, st)
-                c("gemm_fc2_tok", "vtq_gemm", _ptr(ws.h1), 0, _ptr(L.w_fc2), _ptr(L.b_fc2), n_seq, H, self.mlp_dim, dt,
+                  w.ln, dt, st)
+                c("gemm_fc1_tok", "vtq_gemm", w.ln, 0, _ptr(L.w_fc1), _ptr(L.b_fc1), n_seq, self.mlp_dim, H, dt,
+                  EPI_BIAS_GELU_H, w.h1, 0, None, st)
+                c("gemm_fc2_tok", "vtq_gemm", w.h1, 0, _ptr(L.w_fc2), _ptr(L.b_fc2), n_seq, H, self.mlp_dim, dt,
                   EPI_BIAS_RESID_F32, x_tok, S * H, _ptr(L.g2), st)
                 continue
-            c("attention", "vtq_attention_fwd", _ptr(ws.qkv), _ptr(ws.att), n_seq, S, self.heads, dt, 0, st)
+            c("attention", "vtq_attention_fwd", w.qkv, w.att, n_seq, S, self.heads, dt, 0, st)
             if fold:
-                c("gemm_out", "vtq_gemm_ln", _ptr(ws.att), 0, _ptr(L.w_o), _ptr(L.b_o), rows, H, H, dt,
-                  EPI_BIAS_RESID_F32, _ptr(ws.x), 0, _ptr(L.g1), None, 0, None, 0.0, _ptr(ws.ln), _ptr(ws.stats), st)
+                c("gemm_out", "vtq_gemm_ln", w.att, 0, _ptr(L.w_o), _ptr(L.b_o), rows, H, H, dt,
+                  EPI_BIAS_RESID_F32, w.x, 0, _ptr(L.g1), None, 0, None, 0.0, w.ln, w.stats, st)
                 slots_in = ws.ln_slots
-                c("gemm_fc1", "vtq_gemm_ln", _ptr(ws.ln), 0, _ptr(L.w_fc1_f), _ptr(L.b_fc1_f), rows, self.mlp_dim, H,
-                  dt, EPI_BIAS_GELU_H, _ptr(ws.h1), 0, None, _ptr(ws.stats), slots_in, _ptr(L.cs_fc1), eps, None,
+                c("gemm_fc1", "vtq_gemm_ln", w.ln, 0, _ptr(L.w_fc1_f), _ptr(L.b_fc1_f), rows, self.mlp_dim, H,
+                  dt, EPI_BIAS_GELU_H, w.h1, 0, None, w.stats, slots_in, _ptr(L.cs_fc1), eps, None,
                   None, st)
-                c("gemm_fc2", "vtq_gemm_ln", _ptr(ws.h1), 0, _ptr(L.w_fc2), _ptr(L.b_fc2), rows, H, self.mlp_dim, dt,
-                  EPI_BIAS_RESID_F32, _ptr(ws.x), 0, _ptr(L.g2), None, 0, None, 0.0, _ptr(ws.ln), _ptr(ws.stats), st)
+                c("gemm_fc2", "vtq_gemm_ln", w.h1, 0, _ptr(L.w_fc2), _ptr(L.b_fc2), rows, H, self.mlp_dim, dt,
+                  EPI_BIAS_RESID_F32, w.x, 0, _ptr(L.g2), None, 0, None, 0.0, w.ln, w.stats, st)
                 continue
-            c("gemm_out", "vtq_gemm", _ptr(ws.att), 0, _ptr(L.w_o), _ptr(L.b_o), rows, H, H, dt, EPI_BIAS_RESID_F32,
-              _ptr(ws.x), 0, _ptr(L.g1), st)
-            c("layernorm", "vtq_layernorm", _ptr(ws.x), 0, _ptr(L.ln2_w), _ptr(L.ln2_b), eps, rows, H, _ptr(ws.ln), dt, st)
-            c("gemm_fc1", "vtq_gemm", _ptr(ws.ln), 0, _ptr(L.w_fc1), _ptr(L.b_fc1), rows, self.mlp_dim, H, dt,
-              EPI_BIAS_GELU_H, _ptr(ws.h1), 0, None, st)
-            c("gemm_fc2", "vtq_gemm", _ptr(ws.h1), 0, _ptr(L.w_fc2), _ptr(L.b_fc2), rows, H, self.mlp_dim, dt,
-              EPI_BIAS_RESID_F32, _ptr(ws.x), 0, _ptr(L.g2), st)
+            c("gemm_out", "vtq_gemm", w.att, 0, _ptr(L.w_o), _ptr(L.b_o), rows, H, H, dt, EPI_BIAS_RESID_F32,
+              w.x, 0, _ptr(L.g1), st)
+            c("layernorm", "vtq_layernorm", w.x, 0, _ptr(L.ln2_w), _ptr(L.ln2_b), eps, rows, H, w.ln, dt, st)
+            c("gemm_fc1", "vtq_gemm", w.ln, 0, _ptr(L.w_fc1), _ptr(L.b_fc1), rows, self.mlp_dim, H, dt,
+              EPI_BIAS_GELU_H, w.h1, 0, None, st)
+            c("gemm_fc2", "vtq_gemm", w.h1, 0, _ptr(L.w_fc2), _ptr(L.b_fc2), rows, H, self.mlp_dim, dt,
+              EPI_BIAS_RESID_F32, w.x, 0, _ptr(L.g2), st)
+
+    def _encode_and_score(self, ws: _Workspace, embedded: bool, tail: bool = True):
+        """Everything after the inputs sit in ws.patches16 / ws.proj, ws.pos, ws.scales.  ``tail=False`` stops after
+        the encoder with ws.diff = LN(cls_ref) - LN(cls_dist) (no diff_scale): the differentiable tail takes over.
+
+        Sequences are independent until the CLS difference, so with ``split_streams`` the two halves of the sequence
+        batch are encoded as two kernel chains on two streams (joined before cls_diff): the memory-bound kernels of
+        one chain (LayerNorm, embedding) can then share the SMs with the tensor-bound kernels of the other."""
+        c, st = self._call, _stream(self.device)
+        B, S, H = ws.B, ws.S, self.hidden
+        n_seq = ws.streams * B
+        eps = self.ln_eps
+        split = (self.split_streams and self.timeline is None and not self.dump_indices and not self.fuse_layernorm
+                 and n_seq >= 2 and (n_seq // 2) * S >= 256)
+        if split:
+            main = torch.cuda.current_stream(self.device)
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream(device=self.device)
+            side = self._side_stream
+            fork, join = torch.cuda.Event(), torch.cuda.Event()
+            fork.record(main)
+            side.wait_event(fork)
+            h0 = n_seq // 2
+            with torch.cuda.stream(side):
+                self._encode_part(ws, embedded, h0, n_seq - h0, C.c_void_p(side.cuda_stream))
+                join.record(side)
+            self._encode_part(ws, embedded, 0, h0, st)
+            main.wait_event(join)
+        else:
+            self._encode_part(ws, embedded, 0, n_seq, st)
         for k in range(1, ws.streams):   # every distorted block against the (once-encoded) reference block
             c("cls_diff", "vtq_cls_diff", _ptr(ws.x), C.c_void_p(ws.x.data_ptr() + k * B * S * H * 4), B, S, H,
               self.token_num, _ptr(self.lnf_w), _ptr(self.lnf_b), eps, _ptr(self.diff_gamma) if tail else None,
@@ -369,7 +418,7 @@ class Engine:
             if not self.use_cuda_graph or self.dump_indices or self.timeline is not None:
                 self._encode_and_score(ws, embedded, tail)
                 return
-            key = ("emb" if embedded else "patch", self.prune_last_block, self.fuse_layernorm, tail)
+            key = ("emb" if embedded else "patch", self.prune_last_block, self.fuse_layernorm, tail, self.split_streams)
             if ws.graph is None or ws.graph[0] != key:
                 # warm-up outside capture (cudaFuncSetAttribute, lazy module load), then capture
                 self._encode_and_score(ws, embedded, tail)

@@ -60,6 +60,19 @@ def perturbed_grid_samples(batch: int, h: int, w: int, ho: int, wo: int, num_sam
     """
     if num_samples < 1:
         raise ValueError("num_samples must be positive")
+    dev = torch.device(device)
+    if dev.type == "cuda":
+        # one kernel launch per level (vtq_sample_grid: Philox-keyed permutation of the grid cells sorted in shared
+        # memory + jitter); the Philox key is drawn with the caller's generator and never leaves the device
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        dev = torch.device("cuda", idx)
+        key = torch.randint(-2 ** 62, 2 ** 62, (2,), dtype=torch.int64, device=dev, generator=generator)
+        out = torch.empty(batch, 2, num_samples, dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            get_context(idx).call("vtq_sample_grid", _ptr(key), batch, h, w, ho, wo, num_samples,
+                                  float(perturbed_amount), _ptr(out), _stream(dev))
+        return out
+    # host tensors (CPU-side tests of the law): the same law as tensor expressions
     aspect = h / w
     width = max(int(np.ceil(np.sqrt(num_samples / aspect))), 1)
     height = int(np.ceil(width * aspect))
