@@ -69,6 +69,9 @@ static_assert(ATT_SMEM_BYTES <= 227 * 1024, "smem budget");
 #ifndef ATT_POLY_DEG
 #define ATT_POLY_DEG 3
 #endif
+#ifndef ATT_RELAXED_NS
+#define ATT_RELAXED_NS 0   // > 0: TMA producer and epilogue warps sleep this long between barrier probes (A/B)
+#endif
 constexpr uint32_t ATT_TMEM_COLS = 512;
 constexpr uint32_t ATT_TMEM_S = 0;    // + t * 128
 constexpr uint32_t ATT_TMEM_O = 256;  // + t * 64
@@ -80,6 +83,14 @@ constexpr uint32_t ATT_TMEM_P = 384;  // + t * 64: P_t as the K-major A operand 
   do {                                                                                           \
     if (trace != nullptr && blockIdx.x == 0 && (idx) < 512) trace[(role) * 512 + (idx)] = clock64(); \
   } while (0)
+
+__device__ __forceinline__ void att_wait_slack(uint64_t* bar, uint32_t parity) {
+#if ATT_RELAXED_NS > 0
+  mbar_wait_relaxed(bar, parity, ATT_RELAXED_NS);
+#else
+  mbar_wait(bar, parity);
+#endif
+}
 
 // max over 32 scores (columns c0 .. c0+31 of the tile), keys >= kv_valid masked out
 __device__ __forceinline__ void att_fold_max(const uint32_t (&v)[32], int c0, int kv_valid, float& a0, float& a1) {
@@ -196,14 +207,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
           const int seq = w / (nqp * heads);
           const int q0 = qp * (2 * ATT_BQ);
           const uint32_t qb = it & 1;
-          mbar_wait(&q_empty[qb], ((it >> 1) & 1) ^ 1);
+          att_wait_slack(&q_empty[qb], ((it >> 1) & 1) ^ 1);
           mbar_expect_tx(&q_full[qb], 2 * ATT_TILE_BYTES);
           tma_load_3d_hint(sQ + (2 * qb) * ATT_TILE_BYTES, &tmQKV, &q_full[qb], head * ATT_D, q0, seq, hint_qkv);
           tma_load_3d_hint(sQ + (2 * qb + 1) * ATT_TILE_BYTES, &tmQKV, &q_full[qb], head * ATT_D, q0 + ATT_BQ, seq,
                            hint_qkv);
           for (int j = 0; j < nkv; ++j, ++kvc) {
             const uint32_t st = kvc % ATT_KV_STAGES;
-            mbar_wait(&kv_empty[st], ((kvc / ATT_KV_STAGES) & 1) ^ 1);
+            att_wait_slack(&kv_empty[st], ((kvc / ATT_KV_STAGES) & 1) ^ 1);
             mbar_expect_tx(&kv_full[st], 2 * ATT_TILE_BYTES);
             tma_load_3d_hint(sK + st * ATT_TILE_BYTES, &tmQKV, &kv_full[st], hidden + head * ATT_D, j * ATT_BKV, seq,
                              hint_qkv);
@@ -466,10 +477,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         const uint32_t o_row = smem_u32(stage_out) + lane * 128;
         // l_full first: it implies every earlier P_t V of this tile has retired, so the parity wait on pv_done
         // below can only be satisfied by the work item's LAST product
-        mbar_wait(&l_full[t], li & 1);
+        att_wait_slack(&l_full[t], li & 1);
         const float* lp = sL + ((li & 1) * 4 + t * 2) * ATT_BQ + row;
         const float inv_l = __frcp_rn(lp[0] + lp[ATT_BQ]);
-        mbar_wait(&pv_done[t], n_last & 1);
+        att_wait_slack(&pv_done[t], n_last & 1);
         tc_fence_after();
         if (lane == 0) tma_wait_group_read<1>();  // the store that last used this staging block has read it
         __syncwarp();

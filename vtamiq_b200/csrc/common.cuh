@@ -106,6 +106,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Wait for roles with slack (epilogue warps, TMA producers): between two probes the warp really sleeps, so its wait
+// loop does not compete for issue slots with the co-resident working warps.  Wake-up latency up to `sleep_ns`.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t sleep_ns) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t spins = 0;
+  while (true) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(sleep_ns);
+    if (++spins > VTQ_SPIN_LIMIT) __trap();
+  }
+}
+
 // Non-blocking phase probe.  A satisfied mbar_wait still costs a ~100-200 cycle round trip to the barrier unit;
 // issuing the probe early and consuming its result after independent work hides that latency.
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {

@@ -310,10 +310,6 @@ class Engine:
         if not embedded:
             c("gemm_embed", "vtq_gemm", w.patches16, 0, _ptr(self.w_pe), _ptr(self.b_pe), prow, H,
               self.patch_elems, dt, EPI_BIAS_F32, w.proj, 0, None, st)
-        if self.dump_indices:
-            if ws.pos_idx is None:
-                ws.pos_idx = torch.zeros(prow, dtype=torch.int32, device=self.device)
-                ws.scale_idx = torch.zeros(prow, dtype=torch.int32, device=self.device)
         c("embed_assemble", "vtq_embed_assemble", w.proj, w.pos,
           w.scales if self.scale_table is not None else None,
           _ptr(self.pos_table), self.pos_grid, _ptr(self.scale_table), self.num_scales, _ptr(self.cls),
@@ -384,6 +380,9 @@ class Engine:
         B, S, H = ws.B, ws.S, self.hidden
         n_seq = ws.streams * B
         eps = self.ln_eps
+        if self.dump_indices and ws.pos_idx is None:   # (before the buffer views of _encode_part are taken)
+            ws.pos_idx = torch.zeros(n_seq * ws.N, dtype=torch.int32, device=self.device)
+            ws.scale_idx = torch.zeros(n_seq * ws.N, dtype=torch.int32, device=self.device)
         split = (self.split_streams and self.timeline is None and not self.dump_indices and not self.fuse_layernorm
                  and n_seq >= 2 and (n_seq // 2) * S >= 256)
         if split:
