@@ -42,6 +42,9 @@ constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_STAGING_BYTES = GEMM_EPI_WARPS * 4096;  // one 32-row x 128 B staging box per epilogue warp
 constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;
 
+#ifndef VTQ_GEMM_RELAXED_ARRIVE
+#define VTQ_GEMM_RELAXED_ARRIVE 1
+#endif
 #ifndef VTQ_GEMM_F32_NBUF
 #define VTQ_GEMM_F32_NBUF 1   // staging boxes per epilogue warp of the fp32 (residual) epilogue.  2 (two boxes, one pipeline
                               // stage less) measured slower: out-proj 0.060 -> 0.064 ms, fc2 0.146 -> 0.154 ms (r02 notes)
@@ -503,7 +506,14 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
       "{\n\t"
       ".reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+#if VTQ_GEMM_RELAXED_ARRIVE
+      // relaxed: what the leader's MMA thread must not overtake are this warp's tcgen05.ld of the accumulator, and those
+      // have completed (tcgen05.wait::ld) and are ordered by tcgen05.fence::before_thread_sync; no generic-proxy data
+      // travels through this barrier, so the MEMBAR + ERRBAR a release at cluster scope costs per tile buy nothing
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t"
+#else
       "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+#endif
       "}\n" ::"r"(smem_u32(bar)),
       "r"(rank)
       : "memory");
