@@ -126,16 +126,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_row, int row0, int n0, 
       uint32_t r[32];
       tmem_ld32(t_row + c * 32, r);
       tmem_wait_ld();
-      uint8_t* buf = buf0;
-      if constexpr (NBUF == 2) {
-        buf = buf0 + (bc & 1) * 4096;
-        ++bc;
-        if (lane == 0) tma_wait_group_read<1>();  // the store before the previous one has finished reading this box
-      } else {
-        if (lane == 0) tma_wait_group_read<0>();  // the previous store has finished reading the staging box
-      }
-      __syncwarp();
-      const uint32_t row_addr = smem_u32(buf) + lane * 128;
+      // bias / LayerScale first (in place), THEN wait for the staging box: the wait hides under the operand loads
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float4 bv = __ldg(reinterpret_cast<const float4*>(bias + ncol) + j);
@@ -147,9 +138,23 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_row, int row0, int n0, 
           float4 gv = __ldg(reinterpret_cast<const float4*>(gamma + ncol) + j);
           v0 *= gv.x; v1 *= gv.y; v2 *= gv.z; v3 *= gv.w;
         }
-        st_shared_v4(row_addr + ((static_cast<uint32_t>(j) ^ swz) << 4), __float_as_uint(v0), __float_as_uint(v1),
-                     __float_as_uint(v2), __float_as_uint(v3));
+        r[4 * j + 0] = __float_as_uint(v0); r[4 * j + 1] = __float_as_uint(v1);
+        r[4 * j + 2] = __float_as_uint(v2); r[4 * j + 3] = __float_as_uint(v3);
       }
+      uint8_t* buf = buf0;
+      if constexpr (NBUF == 2) {
+        buf = buf0 + (bc & 1) * 4096;
+        ++bc;
+        if (lane == 0) tma_wait_group_read<1>();  // the store before the previous one has finished reading this box
+      } else {
+        if (lane == 0) tma_wait_group_read<0>();  // the previous store has finished reading the staging box
+      }
+      __syncwarp();
+      const uint32_t row_addr = smem_u32(buf) + lane * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        st_shared_v4(row_addr + ((static_cast<uint32_t>(j) ^ swz) << 4), r[4 * j + 0], r[4 * j + 1], r[4 * j + 2],
+                     r[4 * j + 3]);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
@@ -164,10 +169,9 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_row, int row0, int n0, 
     for (int c = half; c < BN / 64; c += 2) {
       const int ncol = n0 + c * 64;
       if (ncol >= N) break;
-      if (lane == 0) tma_wait_group_read<0>();
-      __syncwarp();
       uint8_t* buf = buf0;
       const uint32_t row_addr = smem_u32(buf) + lane * 128;
+      uint32_t pk[16];   // first half of the chunk, packed: it waits in registers for the staging box
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t r[32];
@@ -205,9 +209,24 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_row, int row0, int n0, 
 #pragma unroll
             for (int e = 0; e < 8; e += 2) gelu_erf2(v[e], v[e + 1]);
           }
-          const uint32_t chunk = static_cast<uint32_t>(hh * 4 + j);
-          st_shared_v4(row_addr + ((chunk ^ swz) << 4), pack2<DT>(v[0], v[1]), pack2<DT>(v[2], v[3]),
-                       pack2<DT>(v[4], v[5]), pack2<DT>(v[6], v[7]));
+          if (hh == 0) {
+            pk[4 * j + 0] = pack2<DT>(v[0], v[1]); pk[4 * j + 1] = pack2<DT>(v[2], v[3]);
+            pk[4 * j + 2] = pack2<DT>(v[4], v[5]); pk[4 * j + 3] = pack2<DT>(v[6], v[7]);
+          } else {
+            const uint32_t chunk = static_cast<uint32_t>(4 + j);
+            st_shared_v4(row_addr + ((chunk ^ swz) << 4), pack2<DT>(v[0], v[1]), pack2<DT>(v[2], v[3]),
+                         pack2<DT>(v[4], v[5]), pack2<DT>(v[6], v[7]));
+          }
+        }
+        if (hh == 0) {
+          // the previous store of this warp has finished reading the staging box (the wait hid under the first half's
+          // TMEM load and bias / GELU math)
+          if (lane == 0) tma_wait_group_read<0>();
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            st_shared_v4(row_addr + ((static_cast<uint32_t>(j) ^ swz) << 4), pk[4 * j + 0], pk[4 * j + 1], pk[4 * j + 2],
+                         pk[4 * j + 3]);
         }
       }
       fence_proxy_async_smem();
