@@ -1,6 +1,8 @@
 // HBM-bound row kernels of the path: fp32->16-bit cast, K2 embedding assembly, K4 LayerNorm, K7 quality-token
 // LayerNorm + difference.  (K1 — patch gather, pyramid, uint8 transform — lives in gather.cu.)
 // All are one-pass, coalesced, 128-bit on the wide side; none has data reuse worth staging in smem.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "host.h"
 
@@ -107,42 +109,63 @@ __device__ __forceinline__ float4 ld_f4_hint(const float4* p, uint64_t hint) {
   return v;
 }
 
+// One warp per row, rows in registers, two-pass mean / variance (the reference's arithmetic order per row is kept:
+// results are bit-identical whatever the grid).  A warp walks rows with a grid-wide stride and has the NEXT row's
+// loads in flight while it reduces and writes the current one: the one-row-per-warp version ran at 0.78 of the copy
+// bandwidth (every warp sat out a full DRAM latency between its load and its first add, `long_scoreboard` on the first
+// FADD in ncu), and a LayerNorm launch is 9 % of the cfg2 step.
 template <int DT, int VPL /* float4 per lane */>
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, size_t x_stride,
-                                                        const float* __restrict__ w, const float* __restrict__ b,
-                                                        float eps, size_t rows, void* __restrict__ out16,
-                                                        uint64_t hint_x) {
+__global__ void __launch_bounds__(256, 3) layernorm_kernel(const float* __restrict__ x, size_t x_stride,
+                                                           const float* __restrict__ w, const float* __restrict__ b,
+                                                           float eps, size_t rows, void* __restrict__ out16,
+                                                           uint64_t hint_x) {
   constexpr int HIDDEN = VPL * 128;
   pdl_launch_dependents();
   pdl_wait();
-  const size_t row = blockIdx.x * static_cast<size_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const size_t stride = static_cast<size_t>(gridDim.x) * (blockDim.x >> 5);
+  size_t row = blockIdx.x * static_cast<size_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
-  const float4* src = reinterpret_cast<const float4*>(x + row * x_stride);
-  float4 v[VPL];
-  float s = 0.f;
+  float4 v[VPL], nx[VPL];
+  {
+    const float4* src = reinterpret_cast<const float4*>(x + row * x_stride);
 #pragma unroll
-  for (int k = 0; k < VPL; ++k) v[k] = ld_f4_hint(src + lane + 32 * k, hint_x);  // keep x resident in L2
-#pragma unroll
-  for (int k = 0; k < VPL; ++k) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
-  const float mean = warp_sum(s) * (1.0f / HIDDEN);
-  float q = 0.f;
-#pragma unroll
-  for (int k = 0; k < VPL; ++k) {
-    const float dx = v[k].x - mean, dy = v[k].y - mean, dz = v[k].z - mean, dw = v[k].w - mean;
-    q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    for (int k = 0; k < VPL; ++k) v[k] = ld_f4_hint(src + lane + 32 * k, hint_x);  // keep x resident in L2
   }
-  const float rstd = rsqrtf(warp_sum(q) * (1.0f / HIDDEN) + eps);
-  uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(out16) + row * HIDDEN);
+  while (true) {
+    const size_t next = row + stride;
+    const bool has_next = next < rows;
+    if (has_next) {
+      const float4* src = reinterpret_cast<const float4*>(x + next * x_stride);
 #pragma unroll
-  for (int k = 0; k < VPL; ++k) {
-    const float4 g = __ldg(reinterpret_cast<const float4*>(w) + lane + 32 * k);
-    const float4 be = __ldg(reinterpret_cast<const float4*>(b) + lane + 32 * k);
-    const float y0 = (v[k].x - mean) * rstd * g.x + be.x;
-    const float y1 = (v[k].y - mean) * rstd * g.y + be.y;
-    const float y2 = (v[k].z - mean) * rstd * g.z + be.z;
-    const float y3 = (v[k].w - mean) * rstd * g.w + be.w;
-    __stcg(dst + lane + 32 * k, make_uint2(pack2<DT>(y0, y1), pack2<DT>(y2, y3)));  // L2 only: next GEMM's TMA reads it
+      for (int k = 0; k < VPL; ++k) nx[k] = ld_f4_hint(src + lane + 32 * k, hint_x);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    const float mean = warp_sum(s) * (1.0f / HIDDEN);
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const float dx = v[k].x - mean, dy = v[k].y - mean, dz = v[k].z - mean, dw = v[k].w - mean;
+      q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / HIDDEN) + eps);
+    uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(out16) + row * HIDDEN);
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(w) + lane + 32 * k);
+      const float4 be = __ldg(reinterpret_cast<const float4*>(b) + lane + 32 * k);
+      const float y0 = (v[k].x - mean) * rstd * g.x + be.x;
+      const float y1 = (v[k].y - mean) * rstd * g.y + be.y;
+      const float y2 = (v[k].z - mean) * rstd * g.z + be.z;
+      const float y3 = (v[k].w - mean) * rstd * g.w + be.w;
+      __stcg(dst + lane + 32 * k, make_uint2(pack2<DT>(y0, y1), pack2<DT>(y2, y3)));  // L2 only: next GEMM's TMA reads it
+    }
+    if (!has_next) break;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) v[k] = nx[k];
+    row = next;
   }
 }
 
@@ -286,7 +309,13 @@ extern "C" int vtq_layernorm(vtq_ctx* ctx, const float* x, int64_t x_stride, con
   if (x_stride <= 0) x_stride = hidden;
   VTQ_CHECK_ARG(ctx, x_stride >= hidden && x_stride % 4 == 0, "x_stride must be >= hidden and a multiple of 4");
   if (rows == 0) return VTQ_OK;
-  const unsigned blocks = static_cast<unsigned>((rows + 7) / 8);
+  unsigned blocks = static_cast<unsigned>((rows + 7) / 8);
+  static const int ln_blocks_per_sm = [] {   // resident blocks per SM that walk the rows (0 = one row per warp, A/B)
+    const char* e = std::getenv("VTQ_LN_BLOCKS_PER_SM");
+    return e ? std::atoi(e) : 3;
+  }();
+  if (ln_blocks_per_sm > 0 && blocks > static_cast<unsigned>(ctx->num_sms * ln_blocks_per_sm))
+    blocks = static_cast<unsigned>(ctx->num_sms * ln_blocks_per_sm);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t r = static_cast<size_t>(rows);
   const size_t xs = static_cast<size_t>(x_stride);
