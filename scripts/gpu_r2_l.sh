@@ -1,5 +1,6 @@
 #!/bin/bash
 cd "${GRAFT_REPO_ROOT:-/root/repo}"; mkdir -p gpurun_out
-for v in 0 1 2 4 8 5 3 10 15 7; do
-  env VTQ_DC_DBG=$v timeout 120 python scripts/diffnet_time.py 32 2>&1 | tail -2 | head -1
-done
+for b in 32 1; do
+for g in 96 24 32 48 64 128 148; do
+  env VTQ_DIFFNET_G=$g timeout 120 python scripts/diffnet_time.py $b 2>&1 | tail -1
+done; done

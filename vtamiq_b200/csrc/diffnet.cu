@@ -8,6 +8,8 @@
 // The chain is strictly sequential (each layer needs the complete previous activation), so the whole decoder runs
 // as ONE persistent cooperative kernel with a device-scope barrier between layers (diffnet_fused_kernel).
 // Reference: modules/RCAN/channel_attention.py:13-86, modules/vtamiq/vtamiq.py:12-23,:71-77,:114-117.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "host.h"
 
@@ -267,7 +269,11 @@ static int launch_layer_list(vtq_ctx* ctx, const LayerList& L, int B, int hidden
   const int n_tiles = (B + DENSE_PAIRS - 1) / DENSE_PAIRS;
   int T = n_tiles < 8 ? n_tiles : 8;
   int G = ctx->num_sms / T;
-  if (G > 96) G = 96;
+  static const int g_cap = [] {   // CTAs per column.  Measured at B = 32: 24 -> 0.56 ms, 48 -> 0.39, 64 -> 0.36, 96 -> 0.302,
+    const char* e = std::getenv("VTQ_DIFFNET_G");   // 128 -> 0.294, 148 -> 0.300: per-CTA weight streaming, not the barrier
+    return e ? std::atoi(e) : 128;                  // arrivals, sets the layer time
+  }();
+  if (G > g_cap) G = g_cap;
   if (G < 1) G = 1;
   if (int rc = ensure_dyn_smem(ctx, diffnet_fused_kernel, ctx->smem_optin < 200 * 1024 ? ctx->smem_optin : 200 * 1024,
                                "diffnet: cudaFuncSetAttribute")) return rc;
