@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round 2, run B: bench lines for every BASELINE config + cuBLAS same-shape reference + launch list (baseline of the round).
+# Bench lines for every BASELINE config + same-shape cuBLAS GEMMs next to vtq_gemm.
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 for cfg in cfg2 cfg1 cfg3 cfg4 cfg5; do
