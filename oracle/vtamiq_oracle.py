@@ -70,6 +70,14 @@ def embed(sd, cfg, x, pos, scales):
     return x
 
 
+def _adapter(sd, p, h):
+    """Houlsby adapter h + W2 gelu(W1 h + b1) + b2 (transformer.py:177-194); the VTAMIQ path always uses adapter 0 of a
+    layer when the model has adapters (backbone.py:54-59).  No-op when the layer has none."""
+    if p + "0.weight" not in sd:
+        return h
+    return h + F.linear(F.gelu(F.linear(h, sd[p + "0.weight"], sd[p + "0.bias"])), sd[p + "2.weight"], sd[p + "2.bias"])
+
+
 def encoder_layer(sd, cfg, x, i):
     p = f"transformer.encoder.layers.{i}."
     B, S, H = x.shape
@@ -82,12 +90,14 @@ def encoder_layer(sd, cfg, x, i):
     prob = torch.softmax(torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(HEAD_DIM), dim=-1)
     a = torch.matmul(prob, v).permute(0, 2, 1, 3).contiguous().view(B, S, H)
     a = F.linear(a, sd[p + "attn.out.weight"], sd[p + "attn.out.bias"])
+    a = _adapter(sd, p + "adapter1.adapter.", a)
     if p + "ls1.gamma" in sd:
         a = a * sd[p + "ls1.gamma"]
     x = x + a
     y = F.layer_norm(x, (H,), sd[p + "ffn_norm.weight"], sd[p + "ffn_norm.bias"], LN_EPS)
     y = F.gelu(F.linear(y, sd[p + "ffn.fc1.weight"], sd[p + "ffn.fc1.bias"]))
     y = F.linear(y, sd[p + "ffn.fc2.weight"], sd[p + "ffn.fc2.bias"])
+    y = _adapter(sd, p + "adapter2.adapter.", y)
     if p + "ls2.gamma" in sd:
         y = y * sd[p + "ls2.gamma"]
     return x + y

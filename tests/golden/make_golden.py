@@ -272,6 +272,10 @@ if __name__ == "__main__":
     if "--correlations-only" in sys.argv:
         correlations_case()
         sys.exit(0)
+    if "--adapters-only" in sys.argv:
+        forward_case("adapters", dict(num_keep_layers=3, num_adapters=1, use_layer_scale=True), dict(num_rgs=1, num_rcabs=1),
+                     B=3, H=96, W=128, N=64, n_scales=1, ratio=2.0)
+        sys.exit(0)
     if "--branches-only" in sys.argv:
         patches_branch_case("unaligned", 128, 160, 48, 2, 2.0, seed=7, aligned=False, shuffle=False)
         # randomize_patch_scale_order=True cannot be pinned: under this image's torch (2.11) the reference itself raises
@@ -290,6 +294,8 @@ if __name__ == "__main__":
     forward_case("scales3", dict(num_scales=3), {}, B=2, H=256, W=256, N=100, n_scales=3, ratio=2.0)
     forward_case("traincfg", dict(num_keep_layers=6, num_extra_tokens=8, use_layer_scale=True),
                  dict(ca_reduction=16), B=2, H=96, W=128, N=64, n_scales=1, ratio=2.0)
+    forward_case("adapters", dict(num_keep_layers=3, num_adapters=1, use_layer_scale=True), dict(num_rgs=1, num_rcabs=1),
+                 B=3, H=96, W=128, N=64, n_scales=1, ratio=2.0)
     patches_branch_case("unaligned", 128, 160, 48, 2, 2.0, seed=7, aligned=False, shuffle=False)
     patches_branch_case("weighted", 128, 192, 40, 2, 2.0, seed=9, aligned=True, shuffle=False,
                         sampler_kw=dict(centerbias_weight=0.0, diff_weight=0.6, uniform_weight=0.1, grid_type=1))  # GRID_TYPE_PERTURBED

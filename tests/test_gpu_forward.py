@@ -30,7 +30,7 @@ def _srcc(a, b):
     return float(spearmanr(a, b)[0])
 
 
-@pytest.mark.parametrize("case", ["default", "scales3", "traincfg"])
+@pytest.mark.parametrize("case", ["default", "scales3", "traincfg", "adapters"])
 def test_forward_matches_reference_golden(golden_dir, case):
     g = np.load(os.path.join(golden_dir, f"forward_{case}.npz"))
     m = _build(ast.literal_eval(str(g["vit_cfg"])), ast.literal_eval(str(g["vt_kwargs"])))

@@ -11,7 +11,7 @@ import synth
 from oracle import patch_oracle, vtamiq_oracle
 
 PATCH_CASES = ["single", "multi3", "odd2", "clamp"]
-FORWARD_CASES = ["default", "scales3", "traincfg"]
+FORWARD_CASES = ["default", "scales3", "traincfg", "adapters"]
 
 
 def _load(golden_dir, name):

@@ -56,6 +56,9 @@ class _LayerPack:
     w_fc1_f: torch.Tensor | None = None
     b_fc1_f: torch.Tensor | None = None
     cs_fc1: torch.Tensor | None = None
+    # Houlsby adapters behind the attention / MLP sub-blocks: (W1 16-bit, b1, W2 16-bit, b2, width) or None
+    ad1: tuple | None = None
+    ad2: tuple | None = None
 
 
 def fold_layernorm(w, b, ln_w, ln_b, dtype16):
@@ -246,7 +249,11 @@ class Engine:
                 w_fc1=h16(L.ffn.fc1.weight), b_fc1=f32(L.ffn.fc1.bias),
                 w_fc2=h16(L.ffn.fc2.weight), b_fc2=f32(L.ffn.fc2.bias),
                 g2=f32(L.ls2.gamma) if vit.use_layer_scale else None,
+                # Houlsby adapters: the VTAMIQ path uses adapter pair 0 of a layer (backbone.py:54-59)
+                **(dict(ad1=self._pack_adapter(L.adapters[0][0], h16, f32), ad2=self._pack_adapter(L.adapters[0][1], h16, f32))
+                   if getattr(L, "use_adapters", False) else dict(ad1=None, ad2=None)),
             ))
+        self.use_adapters = bool(getattr(vit, "use_adapters", False))
         self.ln_eps = float(vit.encoder.encoder_norm.eps)
         self.lnf_w, self.lnf_b = f32(vit.encoder.encoder_norm.weight), f32(vit.encoder.encoder_norm.bias)
         self.diff_gamma = f32(m.diff_scale.gamma) if hasattr(m.diff_scale, "gamma") else None
@@ -301,6 +308,25 @@ class Engine:
         self._ws.clear()
 
     # ------------------------------------------------------------------ launch sequence
+    @staticmethod
+    def _pack_adapter(ad, h16, f32):
+        l1, l2 = ad.adapter[0], ad.adapter[2]
+        if l1.weight.shape[0] % 64 or l1.weight.shape[1] % 64:
+            raise VtqError("adapter widths must be multiples of 64 for the GEMM kernels")
+        return (h16(l1.weight), f32(l1.bias), h16(l2.weight), f32(l2.bias), int(l1.weight.shape[0]))
+
+    def _adapter(self, c, w, ad, src16, lds, W, bias, rows, K, gamma, dt, st):
+        """x += gamma * adapter(h) with h = src16 W^T + bias: h is produced once more as a 16-bit matrix (the GEMM
+        operand precision of this engine), then the two adapter GEMMs; the un-adapted branch gamma * h itself was
+        added by the caller's residual GEMM (transformer.py:277-279, :282-284: x + ls(h + adapter(h)))."""
+        w1, b1, w2, b2, width = ad
+        H = self.hidden
+        c("gemm_adapter_in", "vtq_gemm", src16, lds, W, bias, rows, H, K, dt, EPI_BIAS_H, w.ln, 0, None, st)
+        c("gemm_adapter_1", "vtq_gemm", w.ln, 0, _ptr(w1), _ptr(b1), rows, width, H, dt, EPI_BIAS_GELU_H, w.att, 0,
+          None, st)
+        c("gemm_adapter_2", "vtq_gemm", w.att, 0, _ptr(w2), _ptr(b2), rows, H, width, dt, EPI_BIAS_RESID_F32, w.x, 0,
+          gamma, st)
+
     def _encode_part(self, ws: _Workspace, embedded: bool, seq0: int, n_seq: int, st):
         """Patch projection, embedding and the encoder blocks for sequences [seq0, seq0 + n_seq) on stream ``st``."""
         c, dt = self._call, self.vtq16
@@ -319,7 +345,7 @@ class Engine:
         n_layers = len(self.layers)
         # Folded LayerNorms: ws.ln holds the RAW 16-bit copy of x, ws.stats each row's (sum, sum of squares) partials;
         # the residual GEMMs (out-projection, fc2) refresh both, the GEMMs behind a LayerNorm (QKV, fc1) consume them.
-        fold = self.fuse_layernorm and rows >= 256
+        fold = self.fuse_layernorm and rows >= 256 and not self.use_adapters
         slots_in = 1
         if fold:
             c("rowstats_cast", "vtq_rowstats_cast", w.x, rows, H, w.ln, w.stats, dt, st)
@@ -332,7 +358,7 @@ class Engine:
                   dt, st)
                 c("gemm_qkv", "vtq_gemm", w.ln, 0, _ptr(L.w_qkv), _ptr(L.b_qkv), rows, 3 * H, H, dt, EPI_BIAS_H,
                   w.qkv, 0, None, st)
-            if self.prune_last_block and li == n_layers - 1:
+            if self.prune_last_block and li == n_layers - 1 and L.ad1 is None:
                 # Only the quality token of each sequence survives the encoder (transformer.py:634, vtamiq.py:104-108):
                 # in the last block K/V still need every row, but attention output, out-projection, LayerNorm and the
                 # MLP are evaluated for that one row per sequence (row stride S*H picks it out of x / att).
@@ -363,11 +389,15 @@ class Engine:
                 continue
             c("gemm_out", "vtq_gemm", w.att, 0, _ptr(L.w_o), _ptr(L.b_o), rows, H, H, dt, EPI_BIAS_RESID_F32,
               w.x, 0, _ptr(L.g1), st)
+            if L.ad1 is not None:
+                self._adapter(c, w, L.ad1, w.att, 0, _ptr(L.w_o), _ptr(L.b_o), rows, H, _ptr(L.g1), dt, st)
             c("layernorm", "vtq_layernorm", w.x, 0, _ptr(L.ln2_w), _ptr(L.ln2_b), eps, rows, H, w.ln, dt, st)
             c("gemm_fc1", "vtq_gemm", w.ln, 0, _ptr(L.w_fc1), _ptr(L.b_fc1), rows, self.mlp_dim, H, dt,
               EPI_BIAS_GELU_H, w.h1, 0, None, st)
             c("gemm_fc2", "vtq_gemm", w.h1, 0, _ptr(L.w_fc2), _ptr(L.b_fc2), rows, H, self.mlp_dim, dt,
               EPI_BIAS_RESID_F32, w.x, 0, _ptr(L.g2), st)
+            if L.ad2 is not None:
+                self._adapter(c, w, L.ad2, w.h1, 0, _ptr(L.w_fc2), _ptr(L.b_fc2), rows, self.mlp_dim, _ptr(L.g2), dt, st)
 
     def _encode_and_score(self, ws: _Workspace, embedded: bool, tail: bool = True):
         """Everything after the inputs sit in ws.patches16 / ws.proj, ws.pos, ws.scales.  ``tail=False`` stops after

@@ -107,6 +107,20 @@ class MLP(nn.Module):
             nn.init.normal_(fc.bias, std=1e-6)
 
 
+class Adapter(nn.Module):
+    """Houlsby adapter parameters: channels -> channels/4 -> channels (transformer.py:177-194); the constructor draws
+    from the RNG exactly like the reference's (nn.Linear defaults, then xavier + tiny-bias)."""
+
+    def __init__(self, channels, reduction=4):
+        super().__init__()
+        self.adapter = nn.Sequential(nn.Linear(channels, channels // reduction), nn.GELU(),
+                                     nn.Linear(channels // reduction, channels))
+        for layer in self.adapter:
+            if isinstance(layer, nn.Linear):
+                nn.init.xavier_uniform_(layer.weight)
+                nn.init.normal_(layer.bias, std=1e-6)
+
+
 class EncoderLayer(nn.Module):
     """One pre-LN block's parameters (transformer.py:246-273)."""
 
@@ -119,9 +133,13 @@ class EncoderLayer(nn.Module):
         self.ffn = MLP(hidden, cfg["mlp_dim"])
         self.attn = MultiHeadSelfAttention(hidden, cfg["num_heads"])
         self.use_adapters = num_adapters > 0
-        if self.use_adapters:
-            raise NotImplementedError(
-                "vtamiq_b200: encoder adapters (num_adapters>0) are outside the accelerated path")
+        if self.use_adapters:   # same module names / construction order as transformer.py:258-267
+            self.adapters = []
+            for i in range(num_adapters):
+                a1, a2 = Adapter(hidden), Adapter(hidden)
+                self.add_module(f"adapter{2 * i + 1}", a1)
+                self.add_module(f"adapter{2 * i + 2}", a2)
+                self.adapters.append((a1, a2))
         self.ls1 = LayerScale(hidden) if use_layer_scale else nn.Identity()
         self.ls2 = LayerScale(hidden) if use_layer_scale else nn.Identity()
 
