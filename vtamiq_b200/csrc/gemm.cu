@@ -630,9 +630,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = ring + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + GEMM_A_BYTES;
+#if defined(VTQ_GEMM_DIAG_SKIP_A)   // timing diagnostics (wrong results): what bounds the mainloop, fill or smem port?
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::B_BYTES);
+          tma_load_2d_pair(sb, &tmB, &full_bar[stage], kb * GEMM_BK, n0, L2_EVICT_LAST);
+#elif defined(VTQ_GEMM_DIAG_SKIP_B)
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * GEMM_A_BYTES);
+          tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m0, hint_a);
+#else
           if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);  // both CTAs' bytes land here
           tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m0, hint_a);
           tma_load_2d_pair(sb, &tmB, &full_bar[stage], kb * GEMM_BK, n0, L2_EVICT_LAST);  // weights: hot
+#endif
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
