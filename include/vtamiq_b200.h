@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VTQ_ABI_VERSION 4
+#define VTQ_ABI_VERSION 5
 
 enum vtq_status {
   VTQ_OK = 0,
@@ -63,6 +63,13 @@ unsigned long long vtq_launch_count(const vtq_ctx* ctx);
 int vtq_coord_status(vtq_ctx* ctx, int reset);
 /* TMA descriptor cache of this handle (descriptors are encoded once per distinct (pointer, shape, box) and re-used) */
 int vtq_tensor_map_stats(const vtq_ctx* ctx, unsigned long long* hits, unsigned long long* misses);
+/* Traversal direction of the launches that follow on this handle (sticky): 0 = rows / tiles / work items in increasing
+ * order, 1 = decreasing.  Results are identical either way.  A chain of kernels that alternates the direction starts
+ * every kernel on the data its predecessor wrote LAST, which is what is still in the 126 MB L2 (the activations of one
+ * encoder block are 0.65 GB at cfg2): vtq_layernorm, vtq_gemm / vtq_gemm_ln (CTA-pair kernel) and vtq_attention_fwd
+ * honour it; the other entry points ignore it. */
+int vtq_set_reverse(vtq_ctx* ctx, int reverse);
+
 /* bytes of scratch vtq_diffnet_head needs for a batch of B pairs */
 int64_t vtq_workspace_bytes(const vtq_ctx* ctx, int B, int hidden);
 

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("VTQ_LIBRARY") or os.path.join(_HERE, "libvtamiq_b200.
 
 VTQ_F16, VTQ_BF16 = 0, 1
 EPI_BIAS_H, EPI_BIAS_GELU_H, EPI_BIAS_F32, EPI_BIAS_RESID_F32 = 0, 1, 2, 3
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
@@ -26,6 +26,7 @@ SIGNATURES = {
     "vtq_destroy": (_i, [_vp]),
     "vtq_last_error_string": (C.c_char_p, [_vp]),
     "vtq_launch_count": (C.c_ulonglong, [_vp]),
+    "vtq_set_reverse": (_i, [_vp, _i]),
     "vtq_workspace_bytes": (_i64, [_vp, _i, _i]),
     "vtq_patch_gather": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp]),
     "vtq_patch_gather_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp]),

@@ -97,6 +97,12 @@ using namespace vtq;
 
 extern "C" int vtq_abi_version(void) { return VTQ_ABI_VERSION; }
 
+extern "C" int vtq_set_reverse(vtq_ctx* ctx, int reverse) {
+  if (!ctx) return VTQ_ERR_INVALID;
+  ctx->reverse_next = reverse ? 1 : 0;
+  return VTQ_OK;
+}
+
 extern "C" int vtq_create(vtq_ctx** out, int device) {
   if (!out) return VTQ_ERR_INVALID;
   *out = nullptr;

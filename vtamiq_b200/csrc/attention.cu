@@ -137,7 +137,7 @@ __device__ __forceinline__ void att_exp2_poly2(f32x2 x2, float& p0, float& p1) {
 template <int DT, bool TRACE>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
     attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, int S,
-                     int heads, int n_seq, int q_rows, uint64_t hint_qkv, long long* __restrict__ trace) {
+                     int heads, int n_seq, int q_rows, uint64_t hint_qkv, int rev, long long* __restrict__ trace) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B-swizzle atoms need a 1024 B aligned base
   uint8_t* sQ = smem;                                  // [2 buffers][2 tiles]
@@ -203,7 +203,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
       // ------------------------------- TMA producer -------------------------------
       if (lane == 0) {
         uint32_t it = 0, kvc = 0;
-        for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+        for (int w0 = blockIdx.x; w0 < n_items; w0 += gridDim.x, ++it) {
+          const int w = rev ? n_items - 1 - w0 : w0;   // work-item walk direction (vtq_set_reverse)
           const int qp = w % nqp;
           const int head = (w / nqp) % heads;
           const int seq = w / (nqp * heads);
@@ -467,7 +468,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16);
     const uint32_t oswz = static_cast<uint32_t>(lane & 7);
     uint32_t li = 0;
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++li) {
+    for (int w0 = blockIdx.x; w0 < n_items; w0 += gridDim.x, ++li) {
+      const int w = rev ? n_items - 1 - w0 : w0;
       const int qp = w % nqp;
       const int head = (w / nqp) % heads;
       const int seq = w / (nqp * heads);
@@ -567,7 +569,7 @@ int launch_attention(vtq_ctx* ctx, const void* qkv, void* out, int n_seq, int S,
   auto go = [&](auto kern) -> int {
     if (int rc = ensure_dyn_smem(ctx, kern, ATT_SMEM_BYTES, "attention: cudaFuncSetAttribute")) return rc;
     cudaError_t le = launch_pdl(kern, grid, dim3(ATT_THREADS), ATT_SMEM_BYTES, st, tmQKV, tmO, S, heads, n_seq, q_rows,
-                                hint_qkv, trace);
+                                hint_qkv, ctx->reverse_next, trace);
     return le != cudaSuccess ? check_cuda(ctx, le, "attention launch") : VTQ_OK;
   };
   int rc;   // the diagnostic stamps are compiled out of the production kernel (-3.4 % kernel time)

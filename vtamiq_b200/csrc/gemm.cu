@@ -572,7 +572,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
                  const float* __restrict__ bias, const float* __restrict__ gamma, int M, int N, int K, int accumulate,
-                 uint64_t hint_a, uint64_t hint_o, const LnFold ln) {
+                 uint64_t hint_a, uint64_t hint_o, const LnFold ln, int rev) {
   using Cfg = Gemm2Cfg<BN, LN, EPI>;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -623,7 +623,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     // ------------------------------- TMA producer (both CTAs) -------------------
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int t = pair; t < num_tiles; t += num_pairs) {
+      for (int t0 = pair; t0 < num_tiles; t0 += num_pairs) {
+        const int t = rev ? num_tiles - 1 - t0 : t0;   // tile walk direction (vtq_set_reverse)
         const int m0 = (t / num_n) * (2 * GEMM_BM) + static_cast<int>(rank) * GEMM_BM;
         const int n0 = (t % num_n) * BN + static_cast<int>(rank) * (BN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -682,7 +683,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     uint8_t* my_staging = staging + (warp - 2) * 4096 * Cfg::NBUF;
     uint32_t box_counter = 0;  // staging boxes this warp has filled (NBUF == 2: box = counter & 1)
     uint32_t it = 0;
-    for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
+    for (int t0 = pair; t0 < num_tiles; t0 += num_pairs, ++it) {
+      const int t = rev ? num_tiles - 1 - t0 : t0;
       const int m0 = (t / num_n) * (2 * GEMM_BM) + static_cast<int>(rank) * GEMM_BM;
       const int n0 = (t % num_n) * BN;
       const uint32_t acc = it & 1;
@@ -763,7 +765,7 @@ static int launch_2cta(vtq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& 
   const int max_pairs = ctx->num_sms / 2;
   const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;
   cudaError_t le = launch_pdl(kern, dim3(2 * pairs), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, st, tmA, tmB, tmO, tmR, bias,
-                              gamma, M, N, K, accumulate, hint_a, hint_o, ln);
+                              gamma, M, N, K, accumulate, hint_a, hint_o, ln, ctx->reverse_next);
   if (le != cudaSuccess) return check_cuda(ctx, le, "gemm2 launch");
   VTQ_CHECK_LAUNCH(ctx, "gemm2 launch");
   return VTQ_OK;

@@ -29,6 +29,7 @@ struct vtq_ctx {
   std::unordered_set<const void*> smem_configured;
   std::unordered_map<std::string, CUtensorMap> tensor_maps;
   unsigned long long tensor_map_hits = 0, tensor_map_misses = 0;
+  int reverse_next = 0;           // traversal direction of the next row-/tile-walking launches (vtq_set_reverse)
   int diffnet_max_clusters = 0;   // co-resident 16-CTA clusters of the DiffNet kernel (0 = not asked yet, -1 = none)
   int* oob_flag_host = nullptr;  // pinned + mapped: gather kernels set it when a coordinate is out of range
   int* oob_flag_dev = nullptr;

@@ -118,17 +118,22 @@ template <int DT, int VPL /* float4 per lane */>
 __global__ void __launch_bounds__(256, 3) layernorm_kernel(const float* __restrict__ x, size_t x_stride,
                                                            const float* __restrict__ w, const float* __restrict__ b,
                                                            float eps, size_t rows, void* __restrict__ out16,
-                                                           uint64_t hint_x) {
+                                                           uint64_t hint_x, int reverse) {
   constexpr int HIDDEN = VPL * 128;
   pdl_launch_dependents();
   pdl_wait();
   const size_t stride = static_cast<size_t>(gridDim.x) * (blockDim.x >> 5);
   size_t row = blockIdx.x * static_cast<size_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
+  // reverse: walk the rows from the END.  The GEMM in front of a LayerNorm wrote x in increasing row order, so the
+  // last rows are the ones still in L2; and the rows this kernel writes last (the first ones) are what the GEMM
+  // behind it reads first.
+  const size_t flip = reverse ? rows - 1 : 0;
+#define LN_ROW(r) (reverse ? flip - (r) : (r))
   const int lane = threadIdx.x & 31;
   float4 v[VPL], nx[VPL];
   {
-    const float4* src = reinterpret_cast<const float4*>(x + row * x_stride);
+    const float4* src = reinterpret_cast<const float4*>(x + LN_ROW(row) * x_stride);
 #pragma unroll
     for (int k = 0; k < VPL; ++k) v[k] = ld_f4_hint(src + lane + 32 * k, hint_x);  // keep x resident in L2
   }
@@ -136,7 +141,7 @@ __global__ void __launch_bounds__(256, 3) layernorm_kernel(const float* __restri
     const size_t next = row + stride;
     const bool has_next = next < rows;
     if (has_next) {
-      const float4* src = reinterpret_cast<const float4*>(x + next * x_stride);
+      const float4* src = reinterpret_cast<const float4*>(x + LN_ROW(next) * x_stride);
 #pragma unroll
       for (int k = 0; k < VPL; ++k) nx[k] = ld_f4_hint(src + lane + 32 * k, hint_x);
     }
@@ -151,7 +156,7 @@ __global__ void __launch_bounds__(256, 3) layernorm_kernel(const float* __restri
       q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
     }
     const float rstd = rsqrtf(warp_sum(q) * (1.0f / HIDDEN) + eps);
-    uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(out16) + row * HIDDEN);
+    uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(out16) + LN_ROW(row) * HIDDEN);
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
       const float4 g = __ldg(reinterpret_cast<const float4*>(w) + lane + 32 * k);
@@ -167,6 +172,7 @@ __global__ void __launch_bounds__(256, 3) layernorm_kernel(const float* __restri
     for (int k = 0; k < VPL; ++k) v[k] = nx[k];
     row = next;
   }
+#undef LN_ROW
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -316,17 +322,18 @@ extern "C" int vtq_layernorm(vtq_ctx* ctx, const float* x, int64_t x_stride, con
   }();
   if (ln_blocks_per_sm > 0 && blocks > static_cast<unsigned>(ctx->num_sms * ln_blocks_per_sm))
     blocks = static_cast<unsigned>(ctx->num_sms * ln_blocks_per_sm);
+  const int reverse = (ctx->reverse_next && x_stride == hidden) ? 1 : 0;   // dense row blocks only (not strided token rows)
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t r = static_cast<size_t>(rows);
   const size_t xs = static_cast<size_t>(x_stride);
   const uint64_t hint_x = l2_hints_enabled() ? L2_EVICT_LAST : L2_EVICT_NORMAL;
   cudaError_t le;
   if (hidden == 768) {
-    if (dtype == VTQ_F16) le = launch_pdl(layernorm_kernel<DT_F16, 6>, dim3(blocks), dim3(256), 0, st, x, xs, weight, bias, eps, r, out16, hint_x);
-    else le = launch_pdl(layernorm_kernel<DT_BF16, 6>, dim3(blocks), dim3(256), 0, st, x, xs, weight, bias, eps, r, out16, hint_x);
+    if (dtype == VTQ_F16) le = launch_pdl(layernorm_kernel<DT_F16, 6>, dim3(blocks), dim3(256), 0, st, x, xs, weight, bias, eps, r, out16, hint_x, reverse);
+    else le = launch_pdl(layernorm_kernel<DT_BF16, 6>, dim3(blocks), dim3(256), 0, st, x, xs, weight, bias, eps, r, out16, hint_x, reverse);
   } else {
-    if (dtype == VTQ_F16) le = launch_pdl(layernorm_kernel<DT_F16, 8>, dim3(blocks), dim3(256), 0, st, x, xs, weight, bias, eps, r, out16, hint_x);
-    else le = launch_pdl(layernorm_kernel<DT_BF16, 8>, dim3(blocks), dim3(256), 0, st, x, xs, weight, bias, eps, r, out16, hint_x);
+    if (dtype == VTQ_F16) le = launch_pdl(layernorm_kernel<DT_F16, 8>, dim3(blocks), dim3(256), 0, st, x, xs, weight, bias, eps, r, out16, hint_x, reverse);
+    else le = launch_pdl(layernorm_kernel<DT_BF16, 8>, dim3(blocks), dim3(256), 0, st, x, xs, weight, bias, eps, r, out16, hint_x, reverse);
   }
   if (le != cudaSuccess) return check_cuda(ctx, le, "layernorm launch");
   VTQ_CHECK_LAUNCH(ctx, "layernorm launch");

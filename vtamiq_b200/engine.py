@@ -150,6 +150,7 @@ class Engine:
         # two kernel chains (halves of the sequence batch) on two streams inside the captured step: VTQ_SPLIT_STREAMS=1
         self.split_streams = os.environ.get("VTQ_SPLIT_STREAMS", "0") == "1"
         self._side_stream = None
+        self.zigzag = os.environ.get("VTQ_ZIGZAG", "1") == "1"   # alternate the walk direction of consecutive kernels
 
     def _call(self, tag, name, *args):
         """ctx.call, optionally bracketed by CUDA events on the launching stream."""
@@ -333,6 +334,16 @@ class Engine:
         N, S, H = ws.N, ws.S, self.hidden
         rows, prow = n_seq * S, n_seq * N
         w = _WsView(ws, seq0 * N, seq0 * S)
+        # Zig-zag traversal: consecutive row-/tile-walking kernels of the chain alternate their walk direction
+        # (vtq_set_reverse), so each one starts on the rows its predecessor wrote last — the part of the 0.65 GB of
+        # per-block activations that is still in the 126 MB L2.  Results are identical either way.
+        rev = [True]   # the embedding wrote x in increasing row order: the first LayerNorm starts from the end
+
+        def d(tag, name, *args):
+            if self.zigzag:
+                self.ctx.call("vtq_set_reverse", int(rev[0]))
+                rev[0] = not rev[0]
+            c(tag, name, *args)
         if not embedded:
             c("gemm_embed", "vtq_gemm", w.patches16, 0, _ptr(self.w_pe), _ptr(self.b_pe), prow, H,
               self.patch_elems, dt, EPI_BIAS_F32, w.proj, 0, None, st)
@@ -351,12 +362,12 @@ class Engine:
             c("rowstats_cast", "vtq_rowstats_cast", w.x, rows, H, w.ln, w.stats, dt, st)
         for li, L in enumerate(self.layers):
             if fold:
-                c("gemm_qkv", "vtq_gemm_ln", w.ln, 0, _ptr(L.w_qkv_f), _ptr(L.b_qkv_f), rows, 3 * H, H, dt,
+                d("gemm_qkv", "vtq_gemm_ln", w.ln, 0, _ptr(L.w_qkv_f), _ptr(L.b_qkv_f), rows, 3 * H, H, dt,
                   EPI_BIAS_H, w.qkv, 0, None, w.stats, slots_in, _ptr(L.cs_qkv), eps, None, None, st)
             else:
-                c("layernorm", "vtq_layernorm", w.x, 0, _ptr(L.ln1_w), _ptr(L.ln1_b), eps, rows, H, w.ln,
+                d("layernorm", "vtq_layernorm", w.x, 0, _ptr(L.ln1_w), _ptr(L.ln1_b), eps, rows, H, w.ln,
                   dt, st)
-                c("gemm_qkv", "vtq_gemm", w.ln, 0, _ptr(L.w_qkv), _ptr(L.b_qkv), rows, 3 * H, H, dt, EPI_BIAS_H,
+                d("gemm_qkv", "vtq_gemm", w.ln, 0, _ptr(L.w_qkv), _ptr(L.b_qkv), rows, 3 * H, H, dt, EPI_BIAS_H,
                   w.qkv, 0, None, st)
             if self.prune_last_block and li == n_layers - 1 and L.ad1 is None:
                 # Only the quality token of each sequence survives the encoder (transformer.py:634, vtamiq.py:104-108):
@@ -376,28 +387,30 @@ class Engine:
                 c("gemm_fc2_tok", "vtq_gemm", w.h1, 0, _ptr(L.w_fc2), _ptr(L.b_fc2), n_seq, H, self.mlp_dim, dt,
                   EPI_BIAS_RESID_F32, x_tok, S * H, _ptr(L.g2), st)
                 continue
-            c("attention", "vtq_attention_fwd", w.qkv, w.att, n_seq, S, self.heads, dt, 0, st)
+            d("attention", "vtq_attention_fwd", w.qkv, w.att, n_seq, S, self.heads, dt, 0, st)
             if fold:
-                c("gemm_out", "vtq_gemm_ln", w.att, 0, _ptr(L.w_o), _ptr(L.b_o), rows, H, H, dt,
+                d("gemm_out", "vtq_gemm_ln", w.att, 0, _ptr(L.w_o), _ptr(L.b_o), rows, H, H, dt,
                   EPI_BIAS_RESID_F32, w.x, 0, _ptr(L.g1), None, 0, None, 0.0, w.ln, w.stats, st)
                 slots_in = ws.ln_slots
-                c("gemm_fc1", "vtq_gemm_ln", w.ln, 0, _ptr(L.w_fc1_f), _ptr(L.b_fc1_f), rows, self.mlp_dim, H,
+                d("gemm_fc1", "vtq_gemm_ln", w.ln, 0, _ptr(L.w_fc1_f), _ptr(L.b_fc1_f), rows, self.mlp_dim, H,
                   dt, EPI_BIAS_GELU_H, w.h1, 0, None, w.stats, slots_in, _ptr(L.cs_fc1), eps, None,
                   None, st)
-                c("gemm_fc2", "vtq_gemm_ln", w.h1, 0, _ptr(L.w_fc2), _ptr(L.b_fc2), rows, H, self.mlp_dim, dt,
+                d("gemm_fc2", "vtq_gemm_ln", w.h1, 0, _ptr(L.w_fc2), _ptr(L.b_fc2), rows, H, self.mlp_dim, dt,
                   EPI_BIAS_RESID_F32, w.x, 0, _ptr(L.g2), None, 0, None, 0.0, w.ln, w.stats, st)
                 continue
-            c("gemm_out", "vtq_gemm", w.att, 0, _ptr(L.w_o), _ptr(L.b_o), rows, H, H, dt, EPI_BIAS_RESID_F32,
+            d("gemm_out", "vtq_gemm", w.att, 0, _ptr(L.w_o), _ptr(L.b_o), rows, H, H, dt, EPI_BIAS_RESID_F32,
               w.x, 0, _ptr(L.g1), st)
             if L.ad1 is not None:
                 self._adapter(c, w, L.ad1, w.att, 0, _ptr(L.w_o), _ptr(L.b_o), rows, H, _ptr(L.g1), dt, st)
-            c("layernorm", "vtq_layernorm", w.x, 0, _ptr(L.ln2_w), _ptr(L.ln2_b), eps, rows, H, w.ln, dt, st)
-            c("gemm_fc1", "vtq_gemm", w.ln, 0, _ptr(L.w_fc1), _ptr(L.b_fc1), rows, self.mlp_dim, H, dt,
+            d("layernorm", "vtq_layernorm", w.x, 0, _ptr(L.ln2_w), _ptr(L.ln2_b), eps, rows, H, w.ln, dt, st)
+            d("gemm_fc1", "vtq_gemm", w.ln, 0, _ptr(L.w_fc1), _ptr(L.b_fc1), rows, self.mlp_dim, H, dt,
               EPI_BIAS_GELU_H, w.h1, 0, None, st)
-            c("gemm_fc2", "vtq_gemm", w.h1, 0, _ptr(L.w_fc2), _ptr(L.b_fc2), rows, H, self.mlp_dim, dt,
+            d("gemm_fc2", "vtq_gemm", w.h1, 0, _ptr(L.w_fc2), _ptr(L.b_fc2), rows, H, self.mlp_dim, dt,
               EPI_BIAS_RESID_F32, w.x, 0, _ptr(L.g2), st)
             if L.ad2 is not None:
                 self._adapter(c, w, L.ad2, w.h1, 0, _ptr(L.w_fc2), _ptr(L.b_fc2), rows, self.mlp_dim, _ptr(L.g2), dt, st)
+        if self.zigzag:
+            self.ctx.call("vtq_set_reverse", 0)
 
     def _encode_and_score(self, ws: _Workspace, embedded: bool, tail: bool = True):
         """Everything after the inputs sit in ws.patches16 / ws.proj, ws.pos, ws.scales.  ``tail=False`` stops after
@@ -447,7 +460,7 @@ class Engine:
             if not self.use_cuda_graph or self.dump_indices or self.timeline is not None:
                 self._encode_and_score(ws, embedded, tail)
                 return
-            key = ("emb" if embedded else "patch", self.prune_last_block, self.fuse_layernorm, tail, self.split_streams)
+            key = ("emb" if embedded else "patch", self.prune_last_block, self.fuse_layernorm, tail, self.split_streams, self.zigzag)
             if ws.graph is None or ws.graph[0] != key:
                 # warm-up outside capture (cudaFuncSetAttribute, lazy module load), then capture
                 self._encode_and_score(ws, embedded, tail)
