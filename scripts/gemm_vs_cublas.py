@@ -35,6 +35,10 @@ def main():
     ctx = _lib.get_context(0)
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     shapes = [("gemm_qkv", 2304, 768, 0), ("gemm_out", 768, 768, 3), ("gemm_fc1", 3072, 768, 1), ("gemm_fc2", 768, 3072, 3)]
+    only = os.environ.get("GVC_SHAPES")          # e.g. GVC_SHAPES=gemm_out,gemm_fc2
+    if only:
+        shapes = [s for s in shapes if s[0] in only.split(",")]
+    vtq_only = os.environ.get("GVC_VTQ_ONLY") == "1"
     nbuf = 4   # rotate operand / output buffers so that nothing is served from L2 across launches
     for name, N, K, epi in shapes:
         g = torch.Generator(device="cuda").manual_seed(N + K)
@@ -61,6 +65,10 @@ def main():
 
         iters = 50
         t_ours = timeit(ours, iters)
+        if vtq_only:
+            print(json.dumps({"shape": name, "M": M, "N": N, "K": K, "bn_n768": os.environ.get("VTQ_GEMM_BN_N768"),
+                              "vtq_gemm": {"ms": round(t_ours, 4), "tflops": round(2.0 * M * N * K / (t_ours * 1e-3) / 1e12, 1)}}))
+            continue
         t_nt, t_nn, t_lin = timeit(cublas_nt, iters), timeit(cublas_nn, iters), timeit(cublas_linear, iters)
         fl = 2.0 * M * N * K
         tf = lambda ms: round(fl / (ms * 1e-3) / 1e12, 1)

@@ -4,6 +4,11 @@
 # the tracked subset into profiles/).
 cd "${GRAFT_REPO_ROOT:-/root/repo}"; O=gpurun_out/final_r2; mkdir -p $O
 nproc > $O/host.txt; lscpu | grep -E "Model name|^CPU\(s\)" >> $O/host.txt; nvidia-smi -L >> $O/host.txt
+# DRAM traffic of the four encoder projections from a fresh --set full capture (bench.py reports it as roofline.traffic)
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:gemm2_kernel" -s 60 -c 4 -o gpurun_out/prof_gemm2 -f \
+   python bench.py --steps 1 --warmup 1 --no-graph --no-cpu --no-sustained > $O/ncu_gemm2.log 2>&1; echo "=== ncu gemm2 rc=$?"
+python scripts/gemm_traffic.py gpurun_out/prof_gemm2.ncu-rep profiles/gemm_traffic.json && cp profiles/gemm_traffic.json $O/gemm_traffic.json
+python scripts/ncu_summary.py gpurun_out/prof_gemm2.ncu-rep > $O/ncu_gemm2.txt 2>&1
 timeout 2400 python -m pytest tests -q -m gpu -p no:cacheprovider -s --durations=10 2>&1 | tail -60 > $O/pytest_gpu.log
 echo "=== pytest: $(grep -E 'passed|failed|error' $O/pytest_gpu.log | tail -1)"
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "=== smoke rc=$?"; tail -1 $O/smoke.log | cut -c1-300

@@ -3,6 +3,7 @@
 cd "$(dirname "$0")/.."; O=gpurun_out/final_r2; R=r02
 for c in cfg1 cfg2 cfg3 cfg4 cfg5; do cp $O/bench_$c.json profiles/${R}_bench_$c.json; done
 cp $O/bench_cfg2.json profiles/${R}_bench.json
+if [ -f $O/gemm_traffic.json ]; then cp $O/gemm_traffic.json profiles/gemm_traffic.json; cp $O/ncu_gemm2.txt profiles/${R}_ncu_gemm2.txt; fi
 cp $O/bench_reference.json profiles/${R}_bench_reference.json
 cp $O/launches.csv profiles/${R}_launches.csv
 python scripts/launch_summary.py $O/launches.csv > profiles/${R}_launches.md

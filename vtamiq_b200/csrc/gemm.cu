@@ -777,11 +777,34 @@ static int launch_2cta(vtq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& 
 // ~125 cycles per instruction, and a 256 x 128 x 16 instruction is only 64 cycles of tensor work (measured at N = 768:
 // fc2 0.184 ms with BN = 128 vs 0.138 ms with 192 / 256).
 static int pick_bn_pair(int N) {
+  static const int forced768 = [] {   // development knob: VTQ_GEMM_BN_N768=128|192|256 overrides the width for N % 768 == 0
+    const char* e = std::getenv("VTQ_GEMM_BN_N768");
+    return e != nullptr ? std::atoi(e) : 0;
+  }();
+  if (forced768 != 0 && N % 768 == 0 && N < 1536) return forced768;
   if (N % 256 == 0 && (N >= 1536 || N % 192 != 0)) return 256;
   return (N % 192 == 0) ? 192 : 128;
 }
 
 int gemm_ln_slots(int N) { return 2 * ((N + pick_bn_pair(N) - 1) / pick_bn_pair(N)); }
+
+// Width for a plain (no LayerNorm folding) launch, M known.  Where pick_bn_pair says 192 but 256 also divides N (768),
+// 256-wide tiles are the faster ones as soon as the launch is several waves long: a 192-wide tile costs ~0.87 of a
+// 256-wide one (mainloop 72 % vs 82 % tensor-active) for 0.75 of the work.  Measured alone (scripts/gpu_bn768_ab.sh,
+// ms with 192 / 256): attn.out M = 32064 0.0516 / 0.0521, 64128 0.0976 / 0.0929, 1026048 1.55 / 1.35; fc2 0.1366 /
+// 0.1339, 0.2707 / 0.2570, 4.68 / 4.44.  Single-wave launches keep the narrower tile (more CTAs busy).  The folded
+// variants keep pick_bn_pair (their statistics slot count is a function of N alone, vtq_gemm_ln_slots).
+static int pick_bn_pair_m(const vtq_ctx* ctx, int M, int N) {
+  static const bool forced = std::getenv("VTQ_GEMM_BN_N768") != nullptr;
+  const int bn = pick_bn_pair(N);
+  if (bn != 192 || N % 256 != 0 || forced) return bn;
+  const int pairs = ctx->num_sms / 2;
+  const int num_m = (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  const int t192 = num_m * (N / 192), t256 = num_m * (N / 256);
+  if (t192 <= pairs) return bn;
+  const int w192 = (t192 + pairs - 1) / pairs, w256 = (t256 + pairs - 1) / pairs;
+  return (100 * w256 <= 87 * w192) ? 256 : 192;
+}
 
 int launch_gemm(vtq_ctx* ctx, const void* A, int64_t lda, const void* W, const float* bias, int M, int N, int K,
                 int dtype, int epilogue, void* out, int64_t ldo, const float* gamma, cudaStream_t st,
@@ -840,7 +863,7 @@ int launch_gemm(vtq_ctx* ctx, const void* A, int64_t lda, const void* W, const f
     }
   }
   int BN;
-  if (two_cta) BN = pick_bn_pair(N);
+  if (two_cta) BN = (lnargs != nullptr) ? pick_bn_pair(N) : pick_bn_pair_m(ctx, M, N);
   else BN = (N % 256 == 0 && N >= 1536) ? 256 : 128;
 
   CUtensorMap tmA, tmB, tmO;
