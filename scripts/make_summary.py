@@ -33,8 +33,8 @@ w(f"* reference arm ({ref['cpu_baseline']['kind']} of the reference's CPU forwar
   f"cores): {ref['value']:.2f} pairs/s.")
 w(f"* algorithmic work {d['algorithmic_gflop_per_pair']} GFLOP/pair -> {d['achieved_tflops_algorithmic']} TFLOP/s = "
   f"{pk['burst']} of measured bf16 burst, {pk['sustained']} of sustained.")
-w(f"* roofline object ({rf['kernel']}): {rf['achieved']} {rf['unit']} executed, frac {rf['frac']} of sustained / "
-  f"{rf['frac_of_burst']} of burst ({rf['peak_src']}); share of step {rf['share_of_step']}; DRAM traffic per launch "
+w(f"* roofline object ({rf['kernel']}): {rf['achieved']} {rf['unit']} executed, frac {rf['frac']} of {rf['peak']} "
+  f"(= {rf['frac_of_burst']} of burst, {rf['frac_of_sustained']} of sustained; {rf['peak_src']}); share of step {rf['share_of_step']}; DRAM traffic per launch "
   f"{rf['traffic'] / 1e6:.0f} MB vs algorithmic {rf['algorithmic_bytes_per_launch'] / 1e6:.0f} MB.")
 w(f"* clocks during the timed region: {d['clocks']}")
 w(f"* launches per step: {d['launches_per_step']}\n")
