@@ -825,11 +825,27 @@ int launch_gemm(vtq_ctx* ctx, const void* A, int64_t lda, const void* W, const f
                 "pointers must be 16-byte aligned");
   VTQ_CHECK_ARG(ctx, gamma == nullptr || reinterpret_cast<uintptr_t>(gamma) % 16 == 0, "gamma alignment");
 
-  static const bool force_1cta = [] {
+  // Kernel choice.  The CTA-pair kernel (256-row tiles) is the throughput kernel; a launch whose pair tiles do not
+  // even fill one wave of the 74 pairs (the latency configuration: M = 514 rows at cfg1) runs faster as 128-row tiles
+  // on twice as many independent CTAs, as long as those still fit one wave of the 148 SMs: cfg1 step 1.068 -> 1.004 ms,
+  // 2 pairs x 500 patches 1.172 -> 1.107 ms; at 4 pairs x 500 (M = 4008) the 192 single-CTA tiles of fc2 would need two
+  // waves (0.0347 vs 0.0268 ms) and the pair kernel stays (scripts/gpu_cfg1_ab.sh, scripts/gpu_kernel_choice_ab.sh).
+  // VTQ_GEMM_1CTA=1 / =0 force one or the other (development knob); the LayerNorm-folding variants need the pair.
+  static const int forced_kernel = [] {
     const char* e = std::getenv("VTQ_GEMM_1CTA");
-    return e != nullptr && e[0] == '1';
+    return e == nullptr ? -1 : (e[0] == '1' ? 1 : 0);
   }();
-  const bool two_cta = (!force_1cta || lnargs != nullptr) && M >= 2 * GEMM_BM;
+  bool two_cta = M >= 2 * GEMM_BM;
+  if (two_cta && lnargs == nullptr) {
+    if (forced_kernel == 1) two_cta = false;
+    else if (forced_kernel == -1) {
+      const int bn2 = pick_bn_pair_m(ctx, M, N);
+      const int pair_tiles = ((M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * ((N + bn2 - 1) / bn2);
+      const int bn1 = (N % 256 == 0 && N >= 1536) ? 256 : 128;
+      const int single_tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + bn1 - 1) / bn1);
+      two_cta = pair_tiles >= ctx->num_sms / 2 || single_tiles > ctx->num_sms;
+    }
+  }
   LnFold ln = {};
   int ln_mode = LN_NONE;
   if (lnargs != nullptr) {
